@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- env steps/s with full legal masks (20x20, 4 players), BASELINE.json's metric.
+
+One "step" = one ply in every env of the batch: read state + action -> placement, inventory, score,
+next-mover resolution with auto-skip, terminal detection with auto-reset, the next mover's FULL legal
+mask written to HBM, and the next uniform-random legal action sampled on the device (Philox-4x32-10).
+Workload = BASELINE.json configs[1]: 65,536 envs per GPU, random-legal play from reset (weak scaling:
+every rank runs 65,536 envs with global env ids, no collective on the hot path, one NCCL all-reduce of
+the counters at the end).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mask bytes|bits] [--envs E]
+  python bench.py --impl reference ...   # the CPU arm: oracle port on all host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "env steps/s w/ legal masks (20x20 4p)"
+UNIT = "steps/s"
+ALG_BYTES = {"bytes": 31154, "bits": 4529}     # SURVEY.md section 8d / DESIGN.md: algorithmic HBM bytes per env step
+
+
+def host_cores() -> int:
+    return len(os.sched_getaffinity(0))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/blokus_oracle.c, bit-parallel variant) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_random_play(total_plies: int, threads: int, seed: int = 0x5EED):
+    """Uniform-random legal play with full byte masks on `threads` host threads (ctypes releases the GIL).
+    Returns (plies, seconds)."""
+    from oracle.oracle import Oracle
+    orc = Oracle(20, 4)
+    per = max(1, total_plies // threads)
+    states = [orc.new_state() for _ in range(threads)]
+    done = [0] * threads
+
+    def work(i):
+        n, _, _ = orc.random_play(states[i], seed, i, per, auto_reset=True, fast=True, log=False)
+        done[i] = n
+
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return sum(done), time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    per_step = 256 * cores                       # bounded sample: 256 plies per core per "step"
+    cpu_random_play(per_step * max(1, args.warmup), cores)
+    plies, secs = cpu_random_play(per_step * args.steps, cores)
+    v = plies / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "Blokus 20x20 4-player random-legal play with full byte masks, CPU",
+                   "note": "the reference env engine (colosseumrl) is an absent un-vendored dependency; this arm times "
+                           "this repo's C restatement (oracle port, bit-parallel variant), one env per host thread"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{plies} plies of random-legal play ({per_step} per step), one env per thread"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from blokus_rl_b200 import BlokusEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = BlokusEngine(20, 4, device=dev)
+    n, fmt, seed = args.envs, args.mask, 0x5EED
+    base = rank * n                                  # global env ids: results are partition-invariant
+    states = eng.new_states(n)
+    buf = eng.make_buffers(n, fmt, sample=True)
+    act = buf.next_action                            # the step reads action[i] then writes next_action[i]: may alias
+
+    def step():
+        return eng.step(states, act, buffers=buf, mask=fmt, sample=True, seed=seed, env_id_base=base, auto_reset=True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    eng.step(states, None, buffers=buf, mask=fmt, sample=True, seed=seed, env_id_base=base)   # first masks + actions
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- device-resident throughput: K launches, CUDA events on the launching stream ----
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    games = torch.zeros((), dtype=torch.int64, device=dev)
+    evs[0].record()
+    for k in range(args.steps):
+        out = step()
+        evs[k + 1].record()
+    sync_all()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+
+    # ---- end to end through the public API with HOST buffers: pinned actions H2D, results D2H, every step ----
+    h_act = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_flags = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_term = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    h_act.copy_(act, non_blocking=False)
+    e2e_steps = max(4, min(args.steps, 64))
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        act.copy_(h_act, non_blocking=True)                    # host policy's actions -> device
+        out = step()
+        h_act.copy_(out.next_action, non_blocking=True)        # sampled legal actions -> host
+        h_flags.copy_(out.flags, non_blocking=True)            # done / illegal flags -> host
+        h_term.copy_(out.terminal, non_blocking=True)          # terminal vectors (rewards) -> host
+        torch.cuda.current_stream().synchronize()              # the host needs the results to act on them
+    e1.record()
+    sync_all()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+
+    # final counter reduction (the only collective): steps, finished games, illegal flags
+    ctr = torch.tensor([n * args.steps, int((out.flags & 1).sum().item()), int((out.flags & 2).sum().item())],
+                       dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ctr)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * n * args.steps / (total_ms * 1e-3)
+    e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    mean_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
+    achieved = ALG_BYTES[fmt] * n / (mean_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        traffic = json.loads(tf.read_text()).get(f"step_kernel_{fmt}_{n}")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"Blokus 20x20 4-player batched env: step + full legal mask ({fmt}) + on-device random "
+                               f"policy, {n} envs per GPU, auto-reset (BASELINE.json configs[1])",
+                   "envs_per_gpu": n, "mask_format": fmt, "parallelism": f"env-sharded x{world}, no hot-path collective",
+                   "l2": f"per-step working set {(ALG_BYTES[fmt] * n) / 1e6:.0f} MB vs 126 MB L2"
+                         + (" (mask writes evict it every step)" if fmt == "bytes" else " (< L2: states stay L2-resident; see DESIGN.md)")},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n * world,
+                "d2h_bytes_per_step": (4 + 1 + 16) * n * world, "steps": e2e_steps,
+                "note": "pinned host actions H2D -> blk_step -> sampled actions, flags, terminal vectors D2H, sync every step; masks stay on the device for the policy net"},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "step_kernel",
+                     "alg_bytes_per_step": ALG_BYTES[fmt], "mean_launch_ms": mean_launch_ms},
+        "clocks": clocks,
+        "counters": {"steps": int(ctr[0]), "games_finished_last_step": int(ctr[1]), "illegal": int(ctr[2])},
+    }
+    if world == 1 and not args.no_cpu:
+        cores = host_cores()
+        target = 12.0                                         # seconds of CPU work
+        p1, s1 = cpu_random_play(2000 * cores, cores)
+        plies, secs = cpu_random_play(int(p1 / s1 * target), cores)
+        line["cpu_baseline"] = {"value": plies / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{plies} plies of 20x20 4p random-legal play with full byte masks, one env per "
+                                          f"host thread, {secs:.1f} s (oracle port, bit-parallel variant)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mask", default="bytes", choices=["bytes", "bits"])
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

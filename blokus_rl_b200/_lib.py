@@ -1,0 +1,91 @@
+"""ctypes binding of the C ABI in include/blokus_b200.h (libblokus_b200.so, built in-tree by
+``__graft_entry__.build()`` / ``python -m blokus_rl_b200.build``).
+
+There is NO fallback: if the shared library is missing or no B200 is visible, importing the engine
+fails loudly.  The oracle under ``oracle/`` is test infrastructure and is never imported here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libblokus_b200.so"
+
+BLK_MASK_NONE, BLK_MASK_BITS, BLK_MASK_BYTES = 0, 1, 2
+BLK_OPT_AUTO_RESET = 1
+BLK_FLAG_DONE, BLK_FLAG_ILLEGAL = 1, 2
+ABI_VERSION = 1
+
+EXPORTS = (
+    "blk_last_error", "blk_abi_version", "blk_create", "blk_destroy", "blk_get_info", "blk_action_to_cells",
+    "blk_reset", "blk_step", "blk_observe", "blk_board_contents", "blk_game_ended", "blk_rollout",
+)
+
+
+class BlkConfig(C.Structure):
+    _fields_ = [("board_size", C.c_int32), ("num_players", C.c_int32), ("score_rule", C.c_int32),
+                ("device", C.c_int32)]
+
+
+class BlkInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "abi_version", "board_size", "num_players", "num_actions", "num_pieces", "num_orients", "num_fields",
+        "state_words", "mask_words", "mask_bytes", "sm_count")]
+
+
+class BlkStepArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("state_in", C.c_void_p), ("state_out", C.c_void_p), ("action", C.c_void_p),
+        ("mask", C.c_void_p), ("mask_format", C.c_int32), ("mask_stride", C.c_int64),
+        ("legal_count", C.c_void_p), ("terminal", C.c_void_p), ("flags", C.c_void_p), ("scores", C.c_void_p),
+        ("next_action", C.c_void_p), ("seed", C.c_uint64), ("env_id_base", C.c_uint32), ("options", C.c_uint32),
+    ]
+
+
+class BlkRolloutArgs(C.Structure):
+    _fields_ = [
+        ("n_roots", C.c_int64), ("roots", C.c_void_p), ("per_root", C.c_int32), ("seed", C.c_uint64),
+        ("rollout_id_base", C.c_uint32), ("final_scores", C.c_void_p), ("winners", C.c_void_p),
+        ("value_sum", C.c_void_p), ("action_log", C.c_void_p), ("log_stride", C.c_int32), ("plies", C.c_void_p),
+    ]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libblokus_b200.so; raise EngineError (never fall back) when it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise EngineError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.blk_last_error.restype = C.c_char_p
+    lib.blk_create.argtypes = [C.POINTER(BlkConfig), C.POINTER(C.c_void_p)]
+    lib.blk_destroy.argtypes = [C.c_void_p]
+    lib.blk_destroy.restype = None
+    lib.blk_get_info.argtypes = [C.c_void_p, C.POINTER(BlkInfo)]
+    lib.blk_action_to_cells.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+    lib.blk_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.blk_step.argtypes = [C.c_void_p, C.POINTER(BlkStepArgs), C.c_void_p]
+    lib.blk_observe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.blk_board_contents.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.blk_game_ended.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.blk_rollout.argtypes = [C.c_void_p, C.POINTER(BlkRolloutArgs), C.c_void_p]
+    if lib.blk_abi_version() != ABI_VERSION:
+        raise EngineError("libblokus_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise EngineError(f"blokus_b200 error {rc}: {load().blk_last_error().decode()}")

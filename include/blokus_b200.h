@@ -1,0 +1,146 @@
+/*
+ * blokus_b200.h -- C ABI of the B200-native batched Blokus environment engine.
+ *
+ * The reference (KubiakJakub01/Blokus-RL) has no FFI for this path: its env engine is the Python /
+ * Cython package colosseumrl.envs.blokus, called through duck-typed Python at
+ * blokus_rl/colossumrl/blokus_wrapper.py.  Each entry point below names the reference call it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative blk_status otherwise; blk_last_error() gives a
+ *    thread-local message.  No exception crosses the ABI.
+ *  - the caller (PyTorch) owns every device buffer; the engine owns only its constant tables.
+ *  - all work is enqueued asynchronously on the cudaStream_t passed as `void* stream` (NULL = legacy
+ *    default stream); nothing synchronises.
+ *  - one engine handle per process and device; a handle is not thread-safe.
+ *  - there is no CPU fallback: a missing/failed CUDA device is an error.
+ *
+ * State format (uint32 words per env, `state_words` = P*N + P + 4; 88 words = 352 B at 20x20/4p):
+ *    [q*N + y]         row y of player q, bit x = column x
+ *    [P*N + q]         inventory of player q, bit i = piece i still in hand
+ *    [P*N + P]         meta: mover (bits 0-3) | done << 4 | lastmono(q) << (8+q) | ply << 16
+ *    [P*N + P + 1]     game counter (number of auto-resets so far)
+ *    [P*N + P + 2..3]  placed-squares score of players 0..3 as int16, little endian
+ */
+#ifndef BLOKUS_B200_H
+#define BLOKUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLK_ABI_VERSION 1
+
+typedef enum {
+    BLK_OK = 0,
+    BLK_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+    BLK_ERR_CUDA = -2,     /* CUDA runtime error (message has the detail) */
+    BLK_ERR_NODEV = -3     /* no usable sm_100 device */
+} blk_status;
+
+typedef enum { BLK_MASK_NONE = 0, BLK_MASK_BITS = 1, BLK_MASK_BYTES = 2 } blk_mask_format;
+
+/* score_rule: 0 = squares placed (default); 1 = squares placed + 15 when all 21 pieces are placed,
+ * + 5 more when the monomino went last (SURVEY.md Appendix A, R10 is OPEN in the reference). */
+typedef struct {
+    int32_t board_size;    /* N: 5..20 */
+    int32_t num_players;   /* P: 2 or 4 */
+    int32_t score_rule;
+    int32_t device;        /* CUDA device ordinal */
+} blk_config;
+
+typedef struct {
+    int32_t abi_version;
+    int32_t board_size, num_players;
+    int32_t num_actions;   /* A: 30433 at N=20, 2522 at N=7 */
+    int32_t num_pieces;    /* 21 */
+    int32_t num_orients;   /* 91 */
+    int32_t num_fields;    /* (orientation, anchor row) pairs: 1665 at N=20 */
+    int32_t state_words;   /* uint32 words per env state */
+    int32_t mask_words;    /* uint32 words of a bit-packed mask row, padded to 4 (952 at N=20) */
+    int32_t mask_bytes;    /* bytes of a byte-mask row padded to 16 (30448 at N=20) */
+    int32_t sm_count;
+} blk_info;
+
+typedef struct blk_engine blk_engine;
+
+enum { BLK_OPT_AUTO_RESET = 1 };
+enum { BLK_FLAG_DONE = 1, BLK_FLAG_ILLEGAL = 2 };
+
+/* Arguments of blk_step().  Every pointer is a DEVICE pointer; nullable ones are marked. */
+typedef struct {
+    int64_t n;                  /* number of envs */
+    const uint32_t *state_in;   /* [n][state_words] */
+    uint32_t *state_out;        /* [n][state_words]; may alias state_in (in-place) */
+    const int32_t *action;      /* [n] action ids; NULL = do not move, only (re)compute the mover's mask */
+    void *mask;                 /* nullable; next mover's legal mask */
+    int32_t mask_format;        /* blk_mask_format */
+    int64_t mask_stride;        /* row stride: uint32 words for BITS (>= mask_words), bytes for BYTES
+                                   (>= num_actions; multiple of 16 with a 16 B aligned base) */
+    int32_t *legal_count;       /* nullable [n]; number of legal actions of the next mover */
+    float *terminal;            /* nullable [n][P]; 3 / 1 / -1 terminal vector when the step ended the game, else 0 */
+    uint8_t *flags;             /* nullable [n]; BLK_FLAG_* */
+    int16_t *scores;            /* nullable [n][P]; scores after the step (final rule applied; before auto-reset) */
+    int32_t *next_action;       /* nullable [n]; uniform random legal action of the next mover, -1 if none */
+    uint64_t seed;              /* Philox-4x32-10 key = (seed_lo, seed_hi ^ (env_id_base + i)), ctr = (ply, game, 0, 0) */
+    uint32_t env_id_base;       /* global id of env 0 of this batch (multi-GPU sharding keeps results partition-invariant) */
+    uint32_t options;           /* BLK_OPT_* */
+} blk_step_args;
+
+/* Arguments of blk_rollout(): uniform-random playouts to the end of the game, one warp per game. */
+typedef struct {
+    int64_t n_roots;
+    const uint32_t *roots;      /* [n_roots][state_words] */
+    int32_t per_root;           /* playouts per root */
+    uint64_t seed;              /* key = (seed_lo, seed_hi ^ game_index), game_index = rollout_id_base + root*per_root + j; ctr = (ply, 0, 1, 0) */
+    uint32_t rollout_id_base;
+    int16_t *final_scores;      /* [n_roots*per_root][P] */
+    uint8_t *winners;           /* nullable [n_roots*per_root] bitmask of winners */
+    float *value_sum;           /* nullable [n_roots][P]; sum over playouts of the 3/1/-1 terminal vector (atomicAdd; caller zeroes) */
+    uint16_t *action_log;       /* nullable [n_roots*per_root][log_stride]; 0xFFFF terminated */
+    int32_t log_stride;         /* >= 4*21+1 when action_log != NULL */
+    int32_t *plies;             /* nullable [n_roots*per_root] plies played */
+} blk_rollout_args;
+
+const char *blk_last_error(void);
+int blk_abi_version(void);
+
+/* Engine lifetime.  Replaces BlokusEnvironment() at blokus_wrapper.py:42 and the action-table
+ * construction at blokus_wrapper.py:281-324 (tables are built here, deterministically). */
+int blk_create(const blk_config *cfg, blk_engine **out);
+void blk_destroy(blk_engine *h);
+int blk_get_info(const blk_engine *h, blk_info *out);
+
+/* Action table (host side, no GPU work): piece, orientation-within-piece, anchor y, anchor x and the
+ * covered cells (y0,x0,y1,x1,...; `ncells` pairs) of one action id.  Footprint-level view of the ids
+ * built at blokus_wrapper.py:300-316. */
+int blk_action_to_cells(const blk_engine *h, int32_t action, int32_t meta[4], uint8_t cells_yx[10], int32_t *ncells);
+
+/* new_state: blokus_wrapper.py:80-87 (env.new_state()).  Writes n fresh states (game counter 0). */
+int blk_reset(blk_engine *h, uint32_t *state, int64_t n, void *stream);
+
+/* next_state + valid_actions + get_winners fused: blokus_wrapper.py:89-106, 108-132, 164-186.
+ * With args->action == NULL it is valid_actions only (blokus_wrapper.py:122-124). */
+int blk_step(blk_engine *h, const blk_step_args *args, void *stream);
+
+/* canonical_board: blokus_wrapper.py:144-146 -> float32 [n][2P][N][N] (models/blokus_nnet.py:99). */
+int blk_observe(blk_engine *h, const uint32_t *state, float *obs, int64_t n, void *stream);
+
+/* board_contents: blokus_wrapper.py:208-218, 259-266 -> uint8 [n][N][N], 0 empty, 1..P colour. */
+int blk_board_contents(blk_engine *h, const uint32_t *state, uint8_t *board, int64_t n, void *stream);
+
+/* Terminal status of existing states (get_winners without stepping): flags/terminal/scores as in blk_step. */
+int blk_game_ended(blk_engine *h, const uint32_t *state, uint8_t *flags, float *terminal, int16_t *scores,
+                   int64_t n, void *stream);
+
+/* Batched uniform-random playouts (north_star kernel family 4; new capability behind the Player interface,
+ * blokus_rl/players/random_player.py:11-17 repeated to the end of the game). */
+int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOKUS_B200_H */

@@ -1,0 +1,68 @@
+"""CPU tests of the C-ABI boundary: the library loads and exports exactly what include/blokus_b200.h declares.
+No compute call is made (no GPU here)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from blokus_rl_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def declared_functions():
+    text = (ROOT / "include" / "blokus_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(blk_[a-z_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from blokus_rl_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in blokus_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_abi_version_and_struct_sizes(lib):
+    from blokus_rl_b200 import _lib
+    assert lib.blk_abi_version() == 1
+    assert C.sizeof(_lib.BlkConfig) == 16 and C.sizeof(_lib.BlkInfo) == 44
+    assert C.sizeof(_lib.BlkStepArgs) == 112 and C.sizeof(_lib.BlkRolloutArgs) == 88
+
+
+def test_no_cpu_fallback(lib):
+    """Without a GPU the engine must refuse to start instead of silently computing on the host."""
+    import torch
+    from blokus_rl_b200 import BlokusEngine, EngineError, _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(EngineError):
+        BlokusEngine(20, 4)
+    h = C.c_void_p()
+    cfg = _lib.BlkConfig(20, 4, 0, 0)
+    rc = lib.blk_create(C.byref(cfg), C.byref(h))
+    assert rc in (-2, -3) and not h.value
+    assert b"fallback" in lib.blk_last_error() or b"cuda" in lib.blk_last_error().lower()
+
+
+def test_argument_validation_without_gpu(lib):
+    from blokus_rl_b200 import _lib
+    h = C.c_void_p()
+    for bad in (_lib.BlkConfig(21, 4, 0, 0), _lib.BlkConfig(20, 3, 0, 0), _lib.BlkConfig(20, 4, 7, 0)):
+        assert lib.blk_create(C.byref(bad), C.byref(h)) == -1
+    assert lib.blk_step(None, None, None) == -1
+    assert lib.blk_reset(None, None, 0, None) == -1
+
+
+def test_product_package_never_imports_oracle():
+    for f in (ROOT / "blokus_rl_b200").rglob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,213 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) vs the CPU oracle, bit-exact.
+
+PARITY UNPINNED caveat: the oracle restates the reference's contract; the
+reference's own env engine (colosseumrl) is absent and cannot be run.
+"""
+import numpy as np
+import pytest
+
+from helpers import lockstep, unpack_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def test_action_table_matches_oracle(engine20, oracle20, engine7, oracle7):
+    for eng, orc in ((engine20, oracle20), (engine7, oracle7)):
+        assert eng.num_actions == orc.A
+        step = 1 if orc.A < 5000 else 7
+        for a in list(range(0, orc.A, step)) + [orc.A - 1]:
+            meta, cells = eng.action_to_cells(a)
+            ocells, ometa = orc.action_cells(a)
+            assert sorted(cells) == sorted(ocells)
+            assert meta[0] == ometa[0] and meta[2] == ometa[2] and meta[3] == ometa[3]
+
+
+def test_info_and_known_sizes(engine20, engine7):
+    assert engine20.num_actions == 30433          # blokus_rl/models/blokus_nnet.py:17
+    assert engine20.state_words == 88 and engine20.mask_words == 952 and engine20.mask_bytes == 30448
+    assert engine20.info.num_fields == 1665 and engine20.info.num_orients == 91
+    assert engine7.num_actions == 2522
+
+
+def test_reset_and_first_masks(engine20, oracle20):
+    import torch
+    s = engine20.new_states(5)
+    out = engine20.step(s, None, mask="bytes")
+    torch.cuda.synchronize()
+    m = out.mask.cpu().numpy()
+    assert (m.sum(1) == 58).all() and (out.legal_count.cpu().numpy() == 58).all()
+    assert (m[0] == oracle20.legal_mask(oracle20.new_state())).all()
+    assert (s.cpu().numpy().view(np.uint32)[0] == oracle20.pack(oracle20.new_state())).all()
+
+
+def test_lockstep_20x20_autoreset(engine20, oracle20):
+    steps, games = lockstep(engine20, oracle20, n=96, plies=150, seed=0x5EED, check_naive_every=97)
+    assert steps == 96 * 150 and games >= 96
+
+
+def test_lockstep_20x20_no_reset_runs_to_terminal(engine20, oracle20):
+    steps, games = lockstep(engine20, oracle20, n=40, plies=90, seed=7, auto_reset=False, env_id_base=1000)
+    assert games == 40
+
+
+def test_lockstep_7x7_2p(engine7, oracle7):
+    steps, games = lockstep(engine7, oracle7, n=64, plies=60, seed=3, check_naive_every=5)
+    assert games > 64
+
+
+@pytest.mark.parametrize("n,p", [(14, 2), (14, 4), (7, 4), (5, 2), (20, 2)])
+def test_lockstep_other_geometries(n, p):
+    from blokus_rl_b200 import BlokusEngine
+    from oracle.oracle import Oracle
+    eng, orc = BlokusEngine(n, p), Oracle(n, p)
+    lockstep(eng, orc, n=24, plies=70, seed=n * 10 + p, check_naive_every=11)
+    eng.close()
+
+
+def test_bonus_score_rule():
+    from blokus_rl_b200 import BlokusEngine
+    from oracle.oracle import Oracle
+    eng, orc = BlokusEngine(14, 2, score_rule=1), Oracle(14, 2, score_rule=1)
+    lockstep(eng, orc, n=48, plies=80, seed=99)
+    eng.close()
+
+
+def test_illegal_and_out_of_range_actions(engine20, oracle20):
+    import torch
+    s = engine20.new_states(4)
+    before = s.clone()
+    # 0: monomino at (0,0) is legal for player 0; others: far from the corner, out of range, negative
+    acts = torch.tensor([0, 5000, 30433, -1], dtype=torch.int32, device=s.device)
+    out = engine20.step(s, acts, mask="bytes")
+    torch.cuda.synchronize()
+    flags = out.flags.cpu().numpy()
+    assert list(flags) == [0, 2, 2, 2]
+    assert (s[1:] == before[1:]).all() and not (s[0] == before[0]).all()
+    m = out.mask.cpu().numpy()
+    assert (m[1:].sum(1) == 58).all()           # unchanged states still report the mover's mask
+    o = oracle20.new_state(); oracle20.step(o, 0)
+    assert (m[0] == oracle20.legal_mask(o)).all()
+    # overlapping / edge-touching / non-corner placements on a mid-game state
+    o2 = oracle20.new_state()
+    for _ in range(9):
+        oracle20.step(o2, oracle20.sample_action(o2, 1, 0))
+    words = torch.tensor(oracle20.pack(o2).view(np.int32)).cuda().repeat(64, 1).contiguous()
+    rng = np.random.default_rng(0)
+    cand = rng.integers(0, oracle20.A, 64).astype(np.int32)
+    legal = oracle20.legal_mask(o2)
+    out = engine20.step(words, torch.tensor(cand).cuda(), mask=None)
+    torch.cuda.synchronize()
+    got_illegal = (out.flags.cpu().numpy() & 2) != 0
+    assert (got_illegal == (legal[cand] == 0)).all()
+
+
+def test_functional_step_keeps_input(engine20):
+    import torch
+    s = engine20.new_states(3)
+    keep = s.clone()
+    dst = torch.empty_like(s)
+    out = engine20.step(s, torch.zeros(3, dtype=torch.int32, device=s.device), out_states=dst, mask=None)
+    torch.cuda.synchronize()
+    assert (s == keep).all() and not (dst == keep).all() and out.states is dst
+
+
+def test_observation_and_board_contents(engine20, oracle20, engine7, oracle7):
+    import torch
+    for eng, orc in ((engine20, oracle20), (engine7, oracle7)):
+        sts = []
+        for g in range(6):
+            o = orc.new_state()
+            for _ in range(3 + 5 * g):
+                if orc.field(o, "done"):
+                    break
+                orc.step(o, orc.sample_action(o, 5, g))
+            sts.append(o)
+        words = torch.tensor(np.stack([orc.pack(o) for o in sts]).view(np.int32)).cuda()
+        obs = eng.observe(words).cpu().numpy()
+        brd = eng.board_contents(words).cpu().numpy()
+        flags, term, scores = eng.game_ended(words)
+        for i, o in enumerate(sts):
+            assert obs.shape[1:] == (2 * orc.P, orc.N, orc.N)   # blokus_wrapper.py:66-71
+            assert (obs[i] == orc.observe(o)).all()
+            assert (brd[i] == orc.board_contents(o)).all()
+            assert bool(flags[i].item() & 1) == bool(orc.field(o, "done"))
+            assert (scores[i].cpu().numpy() == orc.final_scores(o)[: orc.P]).all()
+            assert (term[i].cpu().numpy() == orc.terminal_values(o)).all()
+
+
+def test_unaligned_and_contiguous_bool_mask(engine20, oracle20):
+    """A caller-provided contiguous bool [n, 30433] buffer (row stride not a multiple of 16) still works."""
+    import torch
+    s = engine20.new_states(3)
+    raw = torch.zeros((3, engine20.num_actions), dtype=torch.uint8, device=s.device)
+    out = engine20.step(s, None, mask=raw)
+    torch.cuda.synchronize()
+    assert (raw[0].cpu().numpy() == oracle20.legal_mask(oracle20.new_state())).all()
+    assert out.mask.shape == (3, engine20.num_actions)
+
+
+def test_rollouts_replay_through_oracle(engine20, oracle20):
+    import torch
+    orc = oracle20
+    roots = []
+    for g in range(6):
+        o = orc.new_state()
+        for _ in range(24):                      # SURVEY.md 8d workload 3: 24 random plies
+            orc.step(o, orc.sample_action(o, 11, g))
+        roots.append(o)
+    words = torch.tensor(np.stack([orc.pack(o) for o in roots]).view(np.int32)).cuda()
+    per_root, seed = 16, 0xABCDEF
+    out = engine20.rollout(words, per_root, seed=seed, log_actions=True)
+    torch.cuda.synchronize()
+    log = out.action_log.cpu().numpy().view(np.uint16)
+    fs = out.final_scores.cpu().numpy()
+    win = out.winners.cpu().numpy()
+    plies = out.plies.cpu().numpy()
+    vsum = out.value_sum.cpu().numpy()
+    for r, root in enumerate(roots):
+        acc = np.zeros(4, np.float32)
+        for j in range(per_root):
+            o = orc.copy(root)
+            gid = r * per_root + j
+            k = 0
+            while not orc.field(o, "done"):
+                a = int(log[r, j, k])
+                assert a == orc.sample_action(o, seed, gid, stream=1), "rollout sampler differs from oracle"
+                assert orc.step(o, a) == 0
+                k += 1
+            assert log[r, j, k] == 0xFFFF and plies[r, j] == k
+            assert (fs[r, j] == orc.final_scores(o)).all()
+            assert win[r, j] == orc.winners(o)
+            acc += orc.terminal_values(o)
+        assert np.allclose(vsum[r], acc)
+
+
+def test_full_size_properties_65536(engine20):
+    """BASELINE config[1] size: 65,536 envs.  Size-independent properties only (no oracle at this size):
+    bytes == unpack(bits), count == popcount, scores == occupied squares, inventories consistent."""
+    import torch
+    eng = engine20
+    n = 65536
+    s = eng.new_states(n)
+    buf = eng.make_buffers(n, "bytes", sample=True)
+    out = eng.step(s, None, buffers=buf, mask="bytes", sample=True, seed=1)
+    for _ in range(40):
+        out = eng.step(s, out.next_action.clone(), buffers=buf, mask="bytes", sample=True, seed=1, auto_reset=True)
+    bits = eng.step(s, None, mask="bits")
+    torch.cuda.synchronize()
+    assert (out.flags & 2).sum().item() == 0
+    idx = torch.randint(0, n, (512,), device=s.device)
+    mb = out.mask[idx].cpu().numpy()
+    assert (unpack_bits(bits.mask[idx].cpu().numpy(), eng.num_actions) == mb).all()
+    assert (out.mask.sum(1) == out.legal_count).all()
+    assert (bits.legal_count == out.legal_count).all()
+    # every chosen action is legal under the mask it was sampled from
+    assert out.mask.gather(1, out.next_action.clamp(min=0).long()[:, None]).all()
+    w = s.cpu().numpy().view(np.uint32)
+    rows = w[:, :80].reshape(n, 4, 20)
+    occupied = np.zeros((n, 4), np.int64)
+    for q in range(4):
+        occupied[:, q] = np.unpackbits(rows[:, q].copy().view(np.uint8), axis=1).sum(1)
+    scores = w[:, 86:88].copy().view(np.int16).reshape(n, 4)
+    assert (scores == occupied).all()
+    assert (rows[:, 0] & rows[:, 1]).sum() == 0 and (rows[:, 2] & rows[:, 3]).sum() == 0
