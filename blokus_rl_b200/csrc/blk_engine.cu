@@ -860,9 +860,14 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     int rc = build_tables(h);
     if (rc != BLK_OK) { blk_destroy(h); return rc; }
     h->step_smem = h->t.bytes + 16 + kWarps * h->g.warp_smem;
-    cudaError_t e1 = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
-    cudaError_t e2 = cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed"); }
+    // the attribute is per function, not per engine: only ever raise it (engines of several board sizes coexist)
+    static int s_max_smem[16] = {0};
+    if (h->step_smem > s_max_smem[cfg->device & 15]) {
+        cudaError_t e1 = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+        cudaError_t e2 = cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed"); }
+        s_max_smem[cfg->device & 15] = h->step_smem;
+    }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_blocks_per_sm, step_kernel, kWarps * 32, h->step_smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, rollout_kernel, kWarps * 32, h->step_smem);
     if (h->step_blocks_per_sm < 1 || h->rollout_blocks_per_sm < 1) { blk_destroy(h); return fail(BLK_ERR_CUDA, "kernel does not fit on an SM"); }
