@@ -79,6 +79,9 @@ struct TableLayout {
     int off_ocells;  // uint32[92]  5 x (dy:3, dx:3)
     int off_foff;    // uint16[nf+1] bit offset (= first action id) of each field, sentinel 0xFFFF
     int off_wsrc;    // uint16[mw]  first field intersecting mask word g
+    int off_wdesc;   // uint32[32*rounds] gather descriptor of mask word g (only when <= 3 fields meet a word):
+                     //   first field (11 bits) | right shift of it (5) | left shift of the 2nd (6) | of the 3rd (6)
+    int off_lut;     // uint2[256]  byte -> 8 bytes of 0/1 (bit i -> byte i)
     int bytes;       // multiple of 16
 };
 
@@ -86,7 +89,9 @@ struct Geometry {
     int N, P, A, nf, mw, mask_bytes, sw, score_rule;
     uint32_t full;      // (1 << N) - 1
     int warp_smem;      // bytes of per-warp scratch (fields + per-word popcounts)
-    int fld_words;
+    int fld_words;      // >= nf + 3; words nf..nf+2 stay zero (gather padding)
+    int rounds;         // ceil(mw / 32): warp-wide passes over the mask words
+    int fast3;          // 1 when every mask word gathers from <= 3 fields (true at N = 20)
 };
 
 struct KParams {
@@ -150,14 +155,54 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
     return c0;
 }
 
-__device__ __forceinline__ uint32_t nib_to_bytes(uint32_t x) {  // 4 bits -> 4 bytes of 0/1
-    return (x * 0x00204081u) & 0x01010101u;
+// k-th (0-based) set bit of w; requires popc(w) > k.  (__fns is emulated with ~500 instructions.)
+__device__ __forceinline__ int kth_set_bit(uint32_t w, int k) {
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const int c = __popc((w >> pos) & ((1u << s) - 1u));
+        if (k >= c) { k -= c; pos += s; }
+    }
+    return pos;
+}
+
+// PTX shl clamps shift amounts above 31 to 32 (result 0); C's << would be undefined there.
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t sh) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));
+    return r;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
 }
 
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kAllLanes, v, d);
     return v;
+}
+
+// Board dimensions as seen by the device helpers.  The kernels are instantiated for <N=20, P=4> (every member a
+// compile-time constant after inlining) and for <0, 0> (runtime values from Geometry).
+struct Dims {
+    int N, P, A, score_rule;
+    uint32_t full;
+};
+template <int kN, int kP>
+__device__ __forceinline__ Dims make_dims(const Geometry &g) {
+    Dims d;
+    d.N = kN ? kN : g.N;
+    d.P = kP ? kP : g.P;
+    d.A = g.A;
+    d.score_rule = g.score_rule;
+    d.full = kN ? ((1u << kN) - 1u) : g.full;
+    return d;
 }
 
 // Per-warp view of one env held in registers (lane y = board row y).
@@ -168,7 +213,7 @@ struct EnvRegs {
     uint32_t meta, game;               // warp-uniform
 };
 
-__device__ __forceinline__ void env_load(EnvRegs &e, const uint32_t *s, const Geometry &g, int lane) {
+__device__ __forceinline__ void env_load(EnvRegs &e, const uint32_t *s, const Dims &g, int lane) {
     const int N = g.N, P = g.P;
     const bool in = lane < N;
     e.own0 = in ? __ldg(s + lane) : 0u;
@@ -186,7 +231,7 @@ __device__ __forceinline__ void env_load(EnvRegs &e, const uint32_t *s, const Ge
     e.sc23 = __shfl_sync(kAllLanes, tail, P + 3);
 }
 
-__device__ __forceinline__ void env_store(const EnvRegs &e, uint32_t *s, const Geometry &g, int lane) {
+__device__ __forceinline__ void env_store(const EnvRegs &e, uint32_t *s, const Dims &g, int lane) {
     const int N = g.N, P = g.P;
     if (lane < N) {
         s[lane] = e.own0;
@@ -207,7 +252,7 @@ __device__ __forceinline__ void env_store(const EnvRegs &e, uint32_t *s, const G
     }
 }
 
-__device__ __forceinline__ void env_fresh(EnvRegs &e, const Geometry &g, uint32_t game) {
+__device__ __forceinline__ void env_fresh(EnvRegs &e, const Dims &g, uint32_t game) {
     e.own0 = e.own1 = e.own2 = e.own3 = 0u;
     e.inv0 = e.inv1 = kFullInv;
     e.inv2 = e.inv3 = g.P > 2 ? kFullInv : 0u;
@@ -217,7 +262,7 @@ __device__ __forceinline__ void env_fresh(EnvRegs &e, const Geometry &g, uint32_
 }
 
 // rows of player q needed for legality: this lane's row of "free" and "diag/corner" boards
-__device__ __forceinline__ void prep_rows(const EnvRegs &e, int q, const Geometry &g, int lane, uint32_t &fr0,
+__device__ __forceinline__ void prep_rows(const EnvRegs &e, int q, const Dims &g, int lane, uint32_t &fr0,
                                           uint32_t &dg0) {
     const uint32_t o = sel4(e.own0, e.own1, e.own2, e.own3, q);
     const uint32_t occ = e.own0 | e.own1 | e.own2 | e.own3;
@@ -238,7 +283,7 @@ __device__ __forceinline__ void prep_rows(const EnvRegs &e, int q, const Geometr
 }
 
 // final-rule score of player q (R10); lastmono/inv decide the optional bonus
-__device__ __forceinline__ int final_score(const EnvRegs &e, int q, const Geometry &g) {
+__device__ __forceinline__ int final_score(const EnvRegs &e, int q, const Dims &g) {
     const uint32_t packed = (q < 2) ? e.sc01 : e.sc23;
     int s = static_cast<int>(static_cast<int16_t>((packed >> (16 * (q & 1))) & 0xffffu));
     if (g.score_rule == 1 && sel4(e.inv0, e.inv1, e.inv2, e.inv3, q) == 0u)
@@ -246,26 +291,42 @@ __device__ __forceinline__ int final_score(const EnvRegs &e, int q, const Geomet
     return s;
 }
 
-// All 91 orientations against the rows in fr[]/dg[]; stages fields, returns this lane's OR of them.
+// All 91 orientations against rows lane..lane+4 of the free / diagonal boards.  Stages one field per
+// (orientation, anchor row = lane) at fld[o*(N+1) - hsum(o) + lane] and returns this lane's OR of them.
+// Every (dy, dx) a 5-cell piece can reach satisfies dy + dx <= 4: 15 shifted copies of each board.
 template <bool kStage>
-__device__ __forceinline__ uint32_t eval_fields(const uint32_t (&fr)[5], const uint32_t (&dg)[5], uint32_t invc,
-                                                uint32_t *fld, int N, int lane) {
+__device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint32_t invc, uint32_t *fld, int N,
+                                                int lane) {
+    uint32_t fs[5][5], ds[5][5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {  // lanes >= N hold 0 and N <= 20, so out-of-range source lanes read 0
+        const uint32_t f = r ? __shfl_down_sync(kAllLanes, fr0, r) : fr0;
+        const uint32_t d = r ? __shfl_down_sync(kAllLanes, dg0, r) : dg0;
+#pragma unroll
+        for (int x = 0; x < 5; ++x) {
+            fs[r][x] = (r + x <= 4) ? (f >> x) : 0u;
+            ds[r][x] = (r + x <= 4) ? (d >> x) : 0u;
+        }
+    }
+    bool ok[6];
+#pragma unroll
+    for (int h = 1; h <= 5; ++h) ok[h] = lane <= N - h;
     uint32_t anyacc = 0u;
     const int np1 = N + 1;
     uint32_t *fldp = fld + lane;
 #define BLK_PIECE_BEGIN(p) if ((invc >> (p)) & 1u) {
-#define BLK_ORIENT(o, p, h, w, n, hsum, y0, x0, y1, x1, y2, x2, y3, x3, y4, x4)                              \
-    {                                                                                                        \
-        const uint32_t f_ = ((fr[y0] >> x0) & (fr[y1] >> x1) & (fr[y2] >> x2) & (fr[y3] >> x3) & (fr[y4] >> x4)) & \
-                            ((dg[y0] >> x0) | (dg[y1] >> x1) | (dg[y2] >> x2) | (dg[y3] >> x3) | (dg[y4] >> x4)); \
-        anyacc |= f_;                                                                                        \
-        if (kStage && lane <= N - (h)) fldp[(o) * np1 - (hsum)] = f_;                                        \
+#define BLK_ORIENT(o, p, h, w, n, hsum, y0, x0, y1, x1, y2, x2, y3, x3, y4, x4)                        \
+    {                                                                                                  \
+        const uint32_t f_ = (fs[y0][x0] & fs[y1][x1] & fs[y2][x2] & fs[y3][x3] & fs[y4][x4]) &         \
+                            (ds[y0][x0] | ds[y1][x1] | ds[y2][x2] | ds[y3][x3] | ds[y4][x4]);         \
+        anyacc |= f_;                                                                                  \
+        if (kStage && ok[h]) fldp[(o) * np1 - (hsum)] = f_;                                            \
     }
 #define BLK_PIECE_ELSE(p) \
     }                     \
     else if (kStage) {
 #define BLK_ZERO(o, h, hsum) \
-    if (lane <= N - (h)) fldp[(o) * np1 - (hsum)] = 0u;
+    if (ok[h]) fldp[(o) * np1 - (hsum)] = 0u;
 #define BLK_PIECE_END(p) }
 #include "blk_orient.inc"
 #undef BLK_PIECE_BEGIN
@@ -276,17 +337,7 @@ __device__ __forceinline__ uint32_t eval_fields(const uint32_t (&fr)[5], const u
     return anyacc;
 }
 
-__device__ __forceinline__ void spread_rows(uint32_t fr0, uint32_t dg0, uint32_t (&fr)[5], uint32_t (&dg)[5]) {
-    fr[0] = fr0;
-    dg[0] = dg0;
-#pragma unroll
-    for (int r = 1; r < 5; ++r) {  // lanes >= N hold 0, and N <= 20, so out-of-range sources read 0
-        fr[r] = __shfl_down_sync(kAllLanes, fr0, r);
-        dg[r] = __shfl_down_sync(kAllLanes, dg0, r);
-    }
-}
-
-// mask word g (bits 32g..32g+31 of the action-id-ordered mask) gathered from the staged fields
+// mask word g (bits 32g..32g+31 of the action-id-ordered mask) gathered from the staged fields: generic form
 __device__ __forceinline__ uint32_t assemble_word(int g, const uint32_t *fld, const uint16_t *foff,
                                                   const uint16_t *wsrc) {
     uint32_t word = 0u;
@@ -302,16 +353,36 @@ __device__ __forceinline__ uint32_t assemble_word(int g, const uint32_t *fld, co
     return word;
 }
 
+// ... and the branch-free form used when at most three fields meet a word (N = 20: fields are 16-20 bits wide)
+__device__ __forceinline__ uint32_t assemble_word3(int g, const uint32_t *fld, const uint32_t *wdesc) {
+    const uint32_t d = wdesc[g];
+    const uint32_t *p = fld + (d & 0x7ffu);
+    return (p[0] >> ((d >> 11) & 31u)) | shl_clamp(p[1], (d >> 16) & 63u) | shl_clamp(p[2], d >> 22);
+}
+
 struct SmemTables {
     const int32_t *obase;
     const uint32_t *oinfo;
     const uint32_t *ocells;
     const uint16_t *foff;
     const uint16_t *wsrc;
+    const uint32_t *wdesc;
+    const uint2 *lut;
 };
+__device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, const TableLayout &t) {
+    SmemTables tb;
+    tb.obase = reinterpret_cast<const int32_t *>(tab + t.off_obase);
+    tb.oinfo = reinterpret_cast<const uint32_t *>(tab + t.off_oinfo);
+    tb.ocells = reinterpret_cast<const uint32_t *>(tab + t.off_ocells);
+    tb.foff = reinterpret_cast<const uint16_t *>(tab + t.off_foff);
+    tb.wsrc = reinterpret_cast<const uint16_t *>(tab + t.off_wsrc);
+    tb.wdesc = reinterpret_cast<const uint32_t *>(tab + t.off_wdesc);
+    tb.lut = reinterpret_cast<const uint2 *>(tab + t.off_lut);
+    return tb;
+}
 
 // decode an action id into this lane's row bits of the footprint; returns false when out of range
-__device__ __forceinline__ bool decode_action(int act, const SmemTables &tb, const Geometry &g, int lane,
+__device__ __forceinline__ bool decode_action(int act, const SmemTables &tb, const Dims &g, int lane,
                                               uint32_t &pm, int &piece, int &ncells) {
     pm = 0u; piece = 0; ncells = 0;
     if (act < 0 || act >= g.A) return false;
@@ -357,7 +428,7 @@ __device__ __forceinline__ void apply_placement(EnvRegs &e, int p, uint32_t pm, 
 }
 
 // winners bitmask + value of lane q (<P): 3 sole winner, 1 tied winner, -1 otherwise (blokus_wrapper.py:177-185)
-__device__ __forceinline__ float terminal_value(const EnvRegs &e, const Geometry &g, int lane, int &my_score) {
+__device__ __forceinline__ float terminal_value(const EnvRegs &e, const Dims &g, int lane, int &my_score) {
     my_score = lane < g.P ? final_score(e, lane, g) : -32768;
     int best = my_score;
 #pragma unroll
@@ -370,33 +441,43 @@ __device__ __forceinline__ float terminal_value(const EnvRegs &e, const Geometry
 // ---------------------------------------------------------------------------------------------
 // step / legal-mask kernel
 // ---------------------------------------------------------------------------------------------
+template <int kN, int kP>
 __global__ void __launch_bounds__(kWarps * 32, 3) step_kernel(const KParams kp) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const Geometry &g = kp.g;
+    const Geometry &gg = kp.g;
+    const Dims g = make_dims<kN, kP>(gg);
     const blk_step_args &a = kp.a;
     unsigned char *tab = smem;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kp.t.bytes);
     unsigned char *scratch = smem + kp.t.bytes + 16;
     tma_load_tables(tab, kp.tables, kp.t.bytes, bar);
-
-    SmemTables tb;
-    tb.obase = reinterpret_cast<const int32_t *>(tab + kp.t.off_obase);
-    tb.oinfo = reinterpret_cast<const uint32_t *>(tab + kp.t.off_oinfo);
-    tb.ocells = reinterpret_cast<const uint32_t *>(tab + kp.t.off_ocells);
-    tb.foff = reinterpret_cast<const uint16_t *>(tab + kp.t.off_foff);
-    tb.wsrc = reinterpret_cast<const uint16_t *>(tab + kp.t.off_wsrc);
+    const SmemTables tb = make_tables(tab, kp.t);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * g.warp_smem);
-    uint8_t *wpop = reinterpret_cast<uint8_t *>(fld + g.fld_words);
     const int N = g.N, P = g.P;
-    const bool vec_ok = a.mask_format == BLK_MASK_BYTES && (a.mask_stride & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0 && a.mask_stride >= g.mask_bytes;
+    const int sw = P * N + P + 4;
+    const int fld_words = kN == 20 ? 1668 : gg.fld_words;
+    const int mw = kN == 20 ? 952 : gg.mw;
+    const int rounds = kN == 20 ? 30 : gg.rounds;
+    const int mask_bytes = kN == 20 ? 30448 : gg.mask_bytes;
+    const bool fast3 = kN == 20 ? true : (gg.fast3 != 0);
+    uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * gg.warp_smem);
+    uint8_t *wpop = reinterpret_cast<uint8_t *>(fld + fld_words);     // 32*rounds bytes, 16 B aligned
+    const int fmt = a.mask_format;
+    const int64_t n = a.n;
+    const int64_t mstride = a.mask_stride;
+    const bool vec_ok = fmt == BLK_MASK_BYTES && (mstride & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0 && mstride >= mask_bytes;
+    const bool want_sample = a.next_action != nullptr;
+    const bool want_words = fmt != BLK_MASK_NONE || a.legal_count != nullptr || want_sample;
+    const uint32_t sh16 = (lane & 1) << 4;
+    const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);
+    for (int i = (kN == 20 ? 1665 : gg.nf) + lane; i < fld_words; i += 32) fld[i] = 0u;   // gather padding stays zero
 
-    for (int64_t env = static_cast<int64_t>(blockIdx.x) * kWarps + warp; env < a.n;
+    for (int64_t env = static_cast<int64_t>(blockIdx.x) * kWarps + warp; env < n;
          env += static_cast<int64_t>(gridDim.x) * kWarps) {
         EnvRegs e;
-        env_load(e, a.state_in + env * g.sw, g, lane);
+        env_load(e, a.state_in + env * sw, g, lane);
         const bool was_done = (e.meta >> 4) & 1u;
         const int mover = e.meta & 15u;
         uint32_t flags = 0u;
@@ -433,10 +514,9 @@ __global__ void __launch_bounds__(kWarps * 32, 3) step_kernel(const KParams kp) 
 #pragma unroll 1
             while (true) {
                 cand = (cand + 1 == P) ? 0 : cand + 1;
-                uint32_t fr0, dg0, fr[5], dg[5];
+                uint32_t fr0, dg0;
                 prep_rows(e, cand, g, lane, fr0, dg0);
-                spread_rows(fr0, dg0, fr, dg);
-                const uint32_t acc = eval_fields<true>(fr, dg, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
+                const uint32_t acc = eval_fields<true>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
                 if (__any_sync(kAllLanes, acc != 0u)) { have = true; break; }
                 if (--tries > 0) continue;
                 if (!moved) break;                      // mask-only call on a state whose mover is stuck
@@ -454,45 +534,44 @@ __global__ void __launch_bounds__(kWarps * 32, 3) step_kernel(const KParams kp) 
         }
         if (ended) flags |= BLK_FLAG_DONE;
         if (!have) {                                   // terminal (or stuck) state: empty mask
-            for (int i = lane; i < g.fld_words; i += 32) fld[i] = 0u;
+            for (int i = lane; i < fld_words; i += 32) fld[i] = 0u;
         }
         __syncwarp();
 
-        // ---- assemble the action-id-ordered mask from the staged fields and stream it out ----
+        // ---- gather the action-id-ordered mask from the staged fields and stream it out ----
         int cnt = 0;
-        const int rounds = (g.mw + 31) >> 5;
-        const bool want_sample = a.next_action != nullptr;
-        if (a.mask_format != BLK_MASK_NONE || a.legal_count != nullptr || want_sample) {
+        if (want_words) {
+            uint8_t *row = reinterpret_cast<uint8_t *>(a.mask) + env * mstride + 16 * lane;
+            uint32_t *wrow = reinterpret_cast<uint32_t *>(a.mask) + env * mstride + lane;
+#pragma unroll 2
             for (int r = 0; r < rounds; ++r) {
                 const int gi = (r << 5) + lane;
-                uint32_t word = 0u;
-                if (gi < g.mw && have) word = assemble_word(gi, fld, tb.foff, tb.wsrc);
+                uint32_t word;
+                if (fast3) word = assemble_word3(gi, fld, tb.wdesc);
+                else word = gi < mw ? assemble_word(gi, fld, tb.foff, tb.wsrc) : 0u;
                 const int pc = __popc(word);
                 cnt += pc;
-                if (want_sample && gi < g.mw) wpop[gi] = static_cast<uint8_t>(pc);
-                if (a.mask_format == BLK_MASK_BITS) {
-                    if (gi < g.mw) reinterpret_cast<uint32_t *>(a.mask)[env * a.mask_stride + gi] = word;
-                } else if (a.mask_format == BLK_MASK_BYTES) {
-                    uint8_t *row = reinterpret_cast<uint8_t *>(a.mask) + env * a.mask_stride;
+                if (want_sample) wpop[gi] = static_cast<uint8_t>(pc);
+                if (fmt == BLK_MASK_BITS) {
+                    if (gi < mw) wrow[r << 5] = word;
+                } else if (fmt == BLK_MASK_BYTES) {
                     if (vec_ok) {
+                        // 32 words -> 1024 bytes; each lane expands 16 bits through the byte LUT and writes 16 B,
+                        // so one warp store covers 512 contiguous bytes
+                        const bool last = r == rounds - 1;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const uint32_t wsrcw = __shfl_sync(kAllLanes, word, 16 * h + (lane >> 1));
-                            const uint32_t bits = (wsrcw >> (16 * (lane & 1))) & 0xffffu;
-                            const int64_t boff = (static_cast<int64_t>(r) << 10) + 512 * h + 16 * lane;
-                            if (boff < g.mask_bytes) {
-                                uint4 v;
-                                v.x = nib_to_bytes(bits & 15u);
-                                v.y = nib_to_bytes((bits >> 4) & 15u);
-                                v.z = nib_to_bytes((bits >> 8) & 15u);
-                                v.w = nib_to_bytes(bits >> 12);
-                                __stcs(reinterpret_cast<uint4 *>(row + boff), v);
-                            }
+                            const uint32_t w2 = __shfl_sync(kAllLanes, word, h ? src_hi : src_lo) >> sh16;
+                            const uint2 lo = tb.lut[w2 & 0xffu], hi = tb.lut[(w2 >> 8) & 0xffu];
+                            const int boff = (r << 10) + 512 * h;
+                            if (!last || boff + 16 * lane < mask_bytes)
+                                __stcs(reinterpret_cast<uint4 *>(row + boff), make_uint4(lo.x, lo.y, hi.x, hi.y));
                         }
                     } else {  // unaligned caller buffer: correct but slow byte stores
+                        uint8_t *urow = reinterpret_cast<uint8_t *>(a.mask) + env * mstride;
                         for (int b = 0; b < 32; ++b) {
                             const int idx = (gi << 5) + b;
-                            if (idx < g.A) row[idx] = static_cast<uint8_t>((word >> b) & 1u);
+                            if (idx < g.A) urow[idx] = static_cast<uint8_t>((word >> b) & 1u);
                         }
                     }
                 }
@@ -509,24 +588,25 @@ __global__ void __launch_bounds__(kWarps * 32, 3) step_kernel(const KParams kp) 
                 const uint32_t u = philox_first(e.meta >> 16, e.game, 0u, 0u, static_cast<uint32_t>(a.seed),
                                                 static_cast<uint32_t>(a.seed >> 32) ^ (a.env_id_base + static_cast<uint32_t>(env)));
                 int k = static_cast<int>(__umulhi(u, static_cast<uint32_t>(cnt)));
-                const int per = rounds;                       // contiguous words per lane
-                int mine = 0;
-                for (int j = 0; j < per; ++j) { const int gi = lane * per + j; if (gi < g.mw) mine += wpop[gi]; }
-                int incl = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(kAllLanes, incl, d); if (lane >= d) incl += t; }
-                const int L = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
-                k -= __shfl_sync(kAllLanes, incl - mine, L);
-                const int gj = L * per + lane;
-                const int c2 = (lane < per && gj < g.mw) ? wpop[gj] : 0;
-                int incl2 = c2;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(kAllLanes, incl2, d); if (lane >= d) incl2 += t; }
+                // level 1: lane r owns pass r (32 words); byte sums via dp4a
+                int tot = 0;
+                if (lane < rounds) {
+                    const uint4 *pp = reinterpret_cast<const uint4 *>(wpop + 32 * lane);
+                    const uint4 x = pp[0], y = pp[1];
+                    tot = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
+                    tot = __dp4a(y.x, 0x01010101u, __dp4a(y.y, 0x01010101u, __dp4a(y.z, 0x01010101u, __dp4a(y.w, 0x01010101u, static_cast<unsigned>(tot)))));
+                }
+                const int incl = warp_incl_scan(tot, lane);
+                const int R = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
+                k -= __shfl_sync(kAllLanes, incl - tot, R);
+                // level 2: the 32 words of pass R
+                const int c2 = wpop[(R << 5) + lane];
+                const int incl2 = warp_incl_scan(c2, lane);
                 const int J = __ffs(__ballot_sync(kAllLanes, k < incl2)) - 1;
                 k -= __shfl_sync(kAllLanes, incl2 - c2, J);
-                const int gsel = L * per + J;
-                const uint32_t word = assemble_word(gsel, fld, tb.foff, tb.wsrc);
-                pick = (gsel << 5) + __fns(word, 0, k + 1);
+                const int gsel = (R << 5) + J;
+                const uint32_t word = fast3 ? assemble_word3(gsel, fld, tb.wdesc) : assemble_word(gsel, fld, tb.foff, tb.wsrc);
+                pick = (gsel << 5) + kth_set_bit(word, k);
             }
             if (lane == 0) a.next_action[env] = pick;
         }
@@ -537,7 +617,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) step_kernel(const KParams kp) 
             if (a.scores != nullptr) a.scores[env * P + lane] = static_cast<int16_t>(fscore);
         }
         if (a.flags != nullptr && lane == 0) a.flags[env] = static_cast<uint8_t>(flags);
-        if (a.state_out != nullptr) env_store(e, a.state_out + env * g.sw, g, lane);
+        if (a.state_out != nullptr) env_store(e, a.state_out + env * sw, g, lane);
         __syncwarp();
     }
 }
@@ -633,47 +713,45 @@ struct RParams {
     Geometry g;
 };
 
+template <int kN, int kP>
 __global__ void __launch_bounds__(kWarps * 32, 3) rollout_kernel(const RParams rp) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const Geometry &g = rp.g;
+    const Geometry &gg = rp.g;
+    const Dims g = make_dims<kN, kP>(gg);
     const blk_rollout_args &a = rp.a;
     unsigned char *tab = smem;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + rp.t.bytes);
     unsigned char *scratch = smem + rp.t.bytes + 16;
     tma_load_tables(tab, rp.tables, rp.t.bytes, bar);
-    SmemTables tb;
-    tb.obase = reinterpret_cast<const int32_t *>(tab + rp.t.off_obase);
-    tb.oinfo = reinterpret_cast<const uint32_t *>(tab + rp.t.off_oinfo);
-    tb.ocells = reinterpret_cast<const uint32_t *>(tab + rp.t.off_ocells);
-    tb.foff = reinterpret_cast<const uint16_t *>(tab + rp.t.off_foff);
-    tb.wsrc = reinterpret_cast<const uint16_t *>(tab + rp.t.off_wsrc);
+    const SmemTables tb = make_tables(tab, rp.t);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * g.warp_smem);
+    uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * gg.warp_smem);
     const int N = g.N, P = g.P;
+    const int sw = P * N + P + 4;
+    const int nf = kN == 20 ? 1665 : gg.nf;
     const int64_t total = a.n_roots * a.per_root;
-    const int per = (g.nf + 31) >> 5;   // contiguous fields per lane for the k-th-bit search
+    const int per = (nf + 31) >> 5;   // contiguous fields per lane for the k-th-bit search (53 at N = 20)
 
     for (int64_t gid = static_cast<int64_t>(blockIdx.x) * kWarps + warp; gid < total;
          gid += static_cast<int64_t>(gridDim.x) * kWarps) {
         const int64_t root = gid / a.per_root;
         EnvRegs e;
-        env_load(e, a.roots + root * g.sw, g, lane);
+        env_load(e, a.roots + root * sw, g, lane);
         const uint32_t key0 = static_cast<uint32_t>(a.seed);
         const uint32_t key1 = static_cast<uint32_t>(a.seed >> 32) ^ (a.rollout_id_base + static_cast<uint32_t>(gid));
         int nply = 0;
         bool over = (e.meta >> 4) & 1u;
-        // the root's mover is trusted to have a move (engine invariant R8); evaluate it first
+        // the root's mover is evaluated first; afterwards every player gets a try after each placement (R8)
         int cand = static_cast<int>(e.meta & 15u);
         cand = cand == 0 ? P - 1 : cand - 1;
         int tries = 1;
 #pragma unroll 1
         while (!over) {
             cand = (cand + 1 == P) ? 0 : cand + 1;
-            uint32_t fr0, dg0, fr[5], dg[5];
+            uint32_t fr0, dg0;
             prep_rows(e, cand, g, lane, fr0, dg0);
-            spread_rows(fr0, dg0, fr, dg);
-            const uint32_t acc = eval_fields<true>(fr, dg, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
+            const uint32_t acc = eval_fields<true>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
             if (!__any_sync(kAllLanes, acc != 0u)) {
                 if (--tries > 0) continue;
                 e.meta |= 1u << 4;
@@ -682,26 +760,22 @@ __global__ void __launch_bounds__(kWarps * 32, 3) rollout_kernel(const RParams r
             }
             __syncwarp();
             e.meta = (e.meta & ~15u) | static_cast<uint32_t>(cand);
-            // count legal actions: lane sums popcounts over its contiguous chunk of fields
+            // count legal actions: lane sums popcounts over its contiguous chunk of fields (field order = id order)
             int mine = 0;
-            for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < g.nf) mine += __popc(fld[i]); }
-            int incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(kAllLanes, incl, d); if (lane >= d) incl += t; }
+            for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
+            const int incl = warp_incl_scan(mine, lane);
             const int cnt = __shfl_sync(kAllLanes, incl, 31);
             const uint32_t u = philox_first(e.meta >> 16, e.game, 1u, 0u, key0, key1);
             int k = static_cast<int>(__umulhi(u, static_cast<uint32_t>(cnt)));
             const int L = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
             k -= __shfl_sync(kAllLanes, incl - mine, L);
-            // second level: the chunk of lane L, up to `per` (<= 64) fields, two per lane
+            // second level: the chunk of lane L, up to `per` (<= 64) fields, 32 at a time
             int fsel = -1, kk = 0;
             for (int half = 0; half * 32 < per; ++half) {
                 const int j = half * 32 + lane;
                 const int i = L * per + j;
-                const int c = (j < per && i < g.nf) ? __popc(fld[i]) : 0;
-                int inc2 = c;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(kAllLanes, inc2, d); if (lane >= d) inc2 += t; }
+                const int c = (j < per && i < nf) ? __popc(fld[i]) : 0;
+                const int inc2 = warp_incl_scan(c, lane);
                 const uint32_t b = __ballot_sync(kAllLanes, k < inc2);
                 if (b) {
                     const int J = __ffs(b) - 1;
@@ -711,7 +785,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) rollout_kernel(const RParams r
                 }
                 k -= __shfl_sync(kAllLanes, inc2, 31);
             }
-            const int act = static_cast<int>(tb.foff[fsel]) + __fns(fld[fsel], 0, kk + 1);
+            const int act = static_cast<int>(tb.foff[fsel]) + kth_set_bit(fld[fsel], kk);
             if (a.action_log != nullptr && lane == 0 && nply < a.log_stride - 1)
                 a.action_log[gid * a.log_stride + nply] = static_cast<uint16_t>(act);
             uint32_t pm; int piece, ncells;
@@ -750,6 +824,9 @@ struct blk_engine {
     int sm_count = 0;
     int step_smem = 0;
     int step_blocks_per_sm = 0, rollout_blocks_per_sm = 0;
+    bool special = false;
+    void (*step_fn)(const KParams) = nullptr;
+    void (*rollout_fn)(const RParams) = nullptr;
     std::vector<int32_t> obase;        // host copies for blk_action_to_cells
     std::vector<int16_t> act_o, act_y, act_x;
 };
@@ -805,6 +882,9 @@ int build_tables(blk_engine *h) {
     t.off_ocells = off; off = align16(off + 4 * (kOrients + 1));
     t.off_foff = off;   off = align16(off + 2 * (g.nf + 1));
     t.off_wsrc = off;   off = align16(off + 2 * g.mw);
+    g.rounds = (g.mw + 31) / 32;
+    t.off_wdesc = off;  off = align16(off + 4 * 32 * g.rounds);
+    t.off_lut = off;    off = align16(off + 8 * 256);
     t.bytes = off;
     std::vector<unsigned char> blob(off, 0);
     memcpy(blob.data() + t.off_obase, h->obase.data(), 4 * (kOrients + 1));
@@ -820,8 +900,34 @@ int build_tables(blk_engine *h) {
     }
     memcpy(blob.data() + t.off_foff, foff.data(), 2 * foff.size());
     memcpy(blob.data() + t.off_wsrc, wsrc.data(), 2 * wsrc.size());
-    g.fld_words = (g.nf + 3) & ~3;
-    g.warp_smem = align16(4 * g.fld_words + g.mw);
+    // gather descriptors: word g = (fld[s] >> r0) | (fld[s+1] << s1) | (fld[s+2] << s2); shifts >= 32 give 0
+    g.fast3 = 1;
+    std::vector<uint32_t> wdesc(32 * g.rounds, static_cast<uint32_t>(g.nf) | (63u << 16) | (63u << 22));
+    for (int w = 0; w < g.mw && g.fast3; ++w) {
+        const int s0 = wsrc[w];
+        if (s0 >= g.nf) continue;                       // padding word: gathers the zero slots behind the fields
+        auto start = [&](int f) { return f < g.nf ? static_cast<int>(foff[f]) : (1 << 20); };   // past the last field: never
+        if (start(s0 + 3) < 32 * w + 32) { g.fast3 = 0; break; }   // a 4th field reaches into this word
+        const int r0 = 32 * w - start(s0);
+        const int s1 = start(s0 + 1) - 32 * w, s2 = start(s0 + 2) - 32 * w;
+        if (r0 < 0 || r0 > 31 || s0 > 0x7ff) { g.fast3 = 0; break; }
+        wdesc[w] = static_cast<uint32_t>(s0) | (static_cast<uint32_t>(r0) << 11) |
+                   (static_cast<uint32_t>(s1 > 63 ? 63 : s1) << 16) | (static_cast<uint32_t>(s2 > 63 ? 63 : s2) << 22);
+    }
+    memcpy(blob.data() + t.off_wdesc, wdesc.data(), 4 * wdesc.size());
+    for (int b = 0; b < 256; ++b) {
+        uint32_t lo = 0, hi = 0;
+        for (int i = 0; i < 4; ++i) {
+            lo |= static_cast<uint32_t>((b >> i) & 1) << (8 * i);
+            hi |= static_cast<uint32_t>((b >> (4 + i)) & 1) << (8 * i);
+        }
+        memcpy(blob.data() + t.off_lut + 8 * b, &lo, 4);
+        memcpy(blob.data() + t.off_lut + 8 * b + 4, &hi, 4);
+    }
+    g.fld_words = (g.nf + 3 + 3) & ~3;                   // >= nf + 3 zero slots for the gather
+    g.warp_smem = align16(4 * g.fld_words + 32 * g.rounds);
+    if (N == 20 && (g.A != 30433 || g.nf != 1665 || g.mw != 952 || g.fld_words != 1668 || !g.fast3))
+        return fail(BLK_ERR_ARG, "internal: N=20 constants in the specialised kernels are stale");
     CUDA_TRY(cudaMalloc(&h->d_tables, off));
     CUDA_TRY(cudaMemcpy(h->d_tables, blob.data(), off, cudaMemcpyHostToDevice));
     return BLK_OK;
@@ -860,16 +966,21 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     int rc = build_tables(h);
     if (rc != BLK_OK) { blk_destroy(h); return rc; }
     h->step_smem = h->t.bytes + 16 + kWarps * h->g.warp_smem;
+    // specialised <20,4> kernels for the headline geometry, runtime-dimension <0,0> kernels for everything else
+    h->special = cfg->board_size == 20 && cfg->num_players == 4;
+    h->step_fn = h->special ? step_kernel<20, 4> : step_kernel<0, 0>;
+    h->rollout_fn = h->special ? rollout_kernel<20, 4> : rollout_kernel<0, 0>;
     // the attribute is per function, not per engine: only ever raise it (engines of several board sizes coexist)
-    static int s_max_smem[16] = {0};
-    if (h->step_smem > s_max_smem[cfg->device & 15]) {
-        cudaError_t e1 = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
-        cudaError_t e2 = cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+    static int s_max_smem[16][2] = {};
+    int &cur_max = s_max_smem[cfg->device & 15][h->special ? 1 : 0];
+    if (h->step_smem > cur_max) {
+        cudaError_t e1 = cudaFuncSetAttribute(h->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+        cudaError_t e2 = cudaFuncSetAttribute(h->rollout_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
         if (e1 != cudaSuccess || e2 != cudaSuccess) { blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed"); }
-        s_max_smem[cfg->device & 15] = h->step_smem;
+        cur_max = h->step_smem;
     }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_blocks_per_sm, step_kernel, kWarps * 32, h->step_smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, rollout_kernel, kWarps * 32, h->step_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_blocks_per_sm, h->step_fn, kWarps * 32, h->step_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, h->rollout_fn, kWarps * 32, h->step_smem);
     if (h->step_blocks_per_sm < 1 || h->rollout_blocks_per_sm < 1) { blk_destroy(h); return fail(BLK_ERR_CUDA, "kernel does not fit on an SM"); }
     *out = h;
     return BLK_OK;
@@ -931,7 +1042,7 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
     KParams kp;
     kp.a = *args; kp.tables = h->d_tables; kp.t = h->t; kp.g = h->g;
     const int grid = grid_for(args->n, kWarps, h->sm_count, h->step_blocks_per_sm);
-    step_kernel<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(kp);
+    h->step_fn<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(kp);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
 }
@@ -982,7 +1093,7 @@ int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream) {
     RParams rp;
     rp.a = *args; rp.tables = h->d_tables; rp.t = h->t; rp.g = h->g;
     const int grid = grid_for(args->n_roots * args->per_root, kWarps, h->sm_count, h->rollout_blocks_per_sm);
-    rollout_kernel<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(rp);
+    h->rollout_fn<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(rp);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
 }
