@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--units", type=float, default=1.0)
     ap.add_argument("--top", type=int, default=45)
     ap.add_argument("--launch", type=int, default=0, help="which captured launch of the kernel")
+    ap.add_argument("--sass-name", default=None, help="substring of the mangled name in the cubin (default: kernel)")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     # split per kernel launch
@@ -68,7 +69,7 @@ def main():
     ci = hdr.index("Instructions Executed")
     cs = hdr.index("# Samples")
     stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-    sass = sass_lines(Path(a.so), a.kernel)
+    sass = sass_lines(Path(a.so), a.sass_name or a.kernel)
     if len(sass) != len(rows):
         print(f"warning: {len(sass)} SASS instructions in the .so vs {len(rows)} in the report (rebuilt since capture?)")
     per_line, per_op, samp_line = Counter(), Counter(), Counter()
