@@ -483,8 +483,8 @@ __global__ void __launch_bounds__(kWarps * 32, 3) step_kernel(const KParams kp) 
         uint32_t flags = 0u;
         bool moved = false;
 
-        if (a.action != nullptr) {
-            const int act = __ldg(a.action + env);
+        const int act = a.action != nullptr ? __ldg(a.action + env) : BLK_ACTION_NONE;
+        if (act != BLK_ACTION_NONE) {
             uint32_t pm; int piece, ncells;
             bool legal = !was_done && decode_action(act, tb, g, lane, pm, piece, ncells);
             if (legal) {

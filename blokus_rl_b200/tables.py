@@ -143,26 +143,47 @@ def action_cells(board_size: int, action: int) -> list[tuple[int, int]]:
     return [(y0 + dy, x0 + dx) for dy, dx in o.cells]
 
 
-def action_to_string(piece_type: int, index: tuple[int, int] | int, orientation: int) -> str:
-    """Engine-defined action string, the analogue of ``colosseumrl.envs.blokus.action_to_string``
-    used at ``blokus_rl/colossumrl/blokus_wrapper.py:310-312``.  The real format is not
-    recoverable (dependency absent); this one is
-    ``"<piece>;<anchor_y>,<anchor_x>;<orientation-within-piece>"``."""
-    if isinstance(index, (tuple, list)):
-        y, x = index
-    else:  # flat index is only meaningful together with a board size; keep it verbatim
-        return f"{piece_type};{index};{orientation}"
-    return f"{piece_type};{y},{x};{orientation}"
+def action_index(board_size: int, orientation: int, y: int, x: int) -> int:
+    """The opaque ``index`` of an action string: ``orientation * N*N + y * N + x``.  Orientation-major on
+    purpose: the reference enumerates ``{piece: {index: [orientation...]}}`` in dict order and numbers
+    the distinct footprints in first-seen order (``blokus_wrapper.py:300-316``); with this key that order
+    IS the canonical id order, so the ids the reference would build equal the engine's."""
+    return (orientation * board_size + y) * board_size + x
+
+
+def action_to_string(piece_type: int, index: int, orientation: int) -> str:
+    """Engine-defined action string, the analogue of ``colosseumrl.envs.blokus.action_to_string`` used at
+    ``blokus_rl/colossumrl/blokus_wrapper.py:310-312``: ``"<piece>;<index>;<orientation-within-piece>"``.
+    The real format is not recoverable (dependency absent); the wrapper treats the
+    string as an opaque dict key, so any injective format is a drop-in."""
+    return f"{piece_type};{index};{orientation}"
 
 
 @lru_cache(maxsize=None)
 def action_strings(board_size: int) -> tuple[str, ...]:
     t = action_table(board_size)
     ors = orientations()
-    return tuple(
-        action_to_string(int(t.action_piece[a]), (int(t.action_y[a]), int(t.action_x[a])),
-                         ors[int(t.action_orient[a])].local)
-        for a in range(t.num_actions))
+    out = []
+    for a in range(t.num_actions):
+        loc = ors[int(t.action_orient[a])].local
+        out.append(action_to_string(int(t.action_piece[a]),
+                                    action_index(board_size, loc, int(t.action_y[a]), int(t.action_x[a])), loc))
+    return tuple(out)
+
+
+@lru_cache(maxsize=None)
+def string_to_action(board_size: int) -> dict:
+    return {s: i for i, s in enumerate(action_strings(board_size))}
+
+
+def write_action_json(path, board_size: int) -> None:
+    """``states/colosseum_{N}_players_{P}.json`` in the reference's cache format ``{action_string: id}``
+    (``blokus_wrapper.py:45-50, 284-288, 321-322``); with it in place the wrapper skips its own enumeration."""
+    import json
+    from pathlib import Path
+    Path(path).parent.mkdir(parents=True, exist_ok=True)
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(string_to_action(board_size), f)
 
 
 def start_corners(board_size: int, num_players: int) -> list[tuple[int, int]]:

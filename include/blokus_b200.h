@@ -68,6 +68,7 @@ typedef struct {
 typedef struct blk_engine blk_engine;
 
 enum { BLK_OPT_AUTO_RESET = 1 };
+#define BLK_ACTION_NONE (-1)   /* per-env "do not move": the env only gets its mask / status refreshed */
 enum { BLK_FLAG_DONE = 1, BLK_FLAG_ILLEGAL = 2 };
 
 /* Arguments of blk_step().  Every pointer is a DEVICE pointer; nullable ones are marked. */
@@ -75,7 +76,7 @@ typedef struct {
     int64_t n;                  /* number of envs */
     const uint32_t *state_in;   /* [n][state_words] */
     uint32_t *state_out;        /* [n][state_words]; may alias state_in (in-place) */
-    const int32_t *action;      /* [n] action ids; NULL = do not move, only (re)compute the mover's mask */
+    const int32_t *action;      /* [n] action ids (BLK_ACTION_NONE = skip this env); NULL = no env moves: mask only */
     void *mask;                 /* nullable; next mover's legal mask */
     int32_t mask_format;        /* blk_mask_format */
     int64_t mask_stride;        /* row stride: uint32 words for BITS (>= mask_words), bytes for BYTES

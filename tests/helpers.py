@@ -48,8 +48,8 @@ def lockstep(eng, orc, n: int, plies: int, seed: int, *, auto_reset: bool = True
             assert (bmask == masks).all(), f"bit mask != byte mask at ply {ply}"
         for i in range(n):
             s = ost[i]
-            if not alive[i]:     # finished without auto-reset: GPU must report an illegal no-op on a done state
-                assert flags[i] == 3 and masks[i].sum() == 0 and nxt[i] == -1
+            if not alive[i]:     # finished without auto-reset: action -1 is a no-op on the done state
+                assert flags[i] == 1 and masks[i].sum() == 0 and nxt[i] == -1
                 assert (orc.pack(s) == words[i]).all()
                 continue
             assert orc.step(s, int(acts[i])) == 0, f"env {i} ply {ply}: GPU action {acts[i]} illegal for oracle"

@@ -77,7 +77,7 @@ def test_illegal_and_out_of_range_actions(engine20, oracle20):
     s = engine20.new_states(4)
     before = s.clone()
     # 0: monomino at (0,0) is legal for player 0; others: far from the corner, out of range, negative
-    acts = torch.tensor([0, 5000, 30433, -1], dtype=torch.int32, device=s.device)
+    acts = torch.tensor([0, 5000, 30433, -7], dtype=torch.int32, device=s.device)
     out = engine20.step(s, acts, mask="bytes")
     torch.cuda.synchronize()
     flags = out.flags.cpu().numpy()
