@@ -85,35 +85,47 @@ def run_reference(args):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Polls NVML (SM clock + clock-event reasons) every 10 ms from a thread DURING the timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index: int):
-        self.rows, self.proc = [], None
+    def __init__(self, torch_index: int):
+        self.sm, self.bits, self.max_mhz, self.h = [], 0, None, None
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(torch_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
+        except Exception as e:                      # noqa: BLE001 - report, never fail the bench on telemetry
+            self.err = repr(e)
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].startswith("Active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self._stop.set()
+        self.t.join(timeout=1)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in self.REASONS.items() if self.bits & b], "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -174,7 +186,7 @@ def run_ours(args):
     h_flags = torch.empty(n, dtype=torch.uint8).pin_memory()
     h_term = torch.empty((n, 4), dtype=torch.float32).pin_memory()
     h_act.copy_(act, non_blocking=False)
-    e2e_steps = max(4, min(args.steps, 64))
+    e2e_steps = max(4, min(args.steps, 256))
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -236,6 +248,8 @@ def run_ours(args):
         "clocks": clocks,
         "counters": {"steps": int(ctr[0]), "games_finished_last_step": int(ctr[1]), "illegal": int(ctr[2])},
     }
+    if world == 1 and not args.no_extra:
+        line["extra"] = extra_workloads(eng, torch)
     if world == 1 and not args.no_cpu:
         cores = host_cores()
         target = 12.0                                         # seconds of CPU work
@@ -249,15 +263,57 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def extra_workloads(eng, torch):
+    """BASELINE.json configs[2] and [3], device-resident, CUDA-event timed (reported next to the headline metric)."""
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    # configs[2]: 1,024 fixed mid-game roots (24 random plies from seeds 0..1023), 1,024 playouts per root to the end
+    roots = eng.new_states(1024)
+    out = eng.step(roots, None, mask=None, sample=True, seed=24)
+    for _ in range(24):
+        out = eng.step(roots, out.next_action, mask=None, sample=True, seed=24)
+    res = {}
+    sec = timed(lambda: res.__setitem__("r", eng.rollout(roots, 1024, seed=7)), 2)
+    plies = float(res["r"].plies.float().mean().item())
+    extra = {"mcts_rollouts_per_s": 1024 * 1024 / sec, "rollout_plies_per_s": 1024 * 1024 * plies / sec,
+             "rollout_workload": "1024 roots after 24 random plies x 1024 uniform-random playouts to terminal",
+             "rollout_mean_plies": plies}
+    # configs[3]: batched leaf expansion feeding the torch net: obs f32 [B,8,20,20] + bool mask [B,30433] + terminal vectors
+    for B in (256, 4096):
+        leaves = eng.new_states(B)
+        o = eng.step(leaves, None, mask=None, sample=True, seed=3)
+        for _ in range(20):
+            o = eng.step(leaves, o.next_action, mask=None, sample=True, seed=3)
+        buf = eng.make_buffers(B, "bytes")
+        obs = torch.empty((B, 8, 20, 20), dtype=torch.float32, device=leaves.device)
+
+        def expand():
+            eng.step(leaves, None, buffers=buf, mask="bytes")
+            eng.observe(leaves, out=obs)
+        sec = timed(expand, 20)
+        extra[f"leaf_expansions_per_s_B{B}"] = B / sec
+    return extra
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mask", default="bytes", choices=["bytes", "bits"])
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the rollout / leaf-expansion extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
