@@ -10,7 +10,8 @@ import ctypes as C
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libblokus_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ.get("BLOKUS_B200_LIB", _PKG / "libblokus_b200.so"))   # override: A/B kernel experiments only
 
 BLK_MASK_NONE, BLK_MASK_BITS, BLK_MASK_BYTES = 0, 1, 2
 BLK_OPT_AUTO_RESET = 1

@@ -32,9 +32,33 @@ constexpr int kMaxN = 20;
 constexpr int kPieces = 21;
 constexpr int kOrients = 91;
 constexpr int kSumH = 246;  // sum of bounding-box heights over the 91 orientations
-constexpr int kWarps = 8;   // warps (= envs in flight) per block
+#ifndef BLK_WARPS
+#define BLK_WARPS 8
+#define BLK_MIN_BLOCKS 3
+#endif
+constexpr int kWarps = BLK_WARPS;   // warps (= envs in flight) per block
 constexpr uint32_t kFullInv = (1u << kPieces) - 1u;
 constexpr uint32_t kAllLanes = 0xffffffffu;
+#ifndef BLK_ST_POLICY
+#define BLK_ST_POLICY 1
+#endif
+#if BLK_ST_POLICY == 0
+#define BLK_STORE16(p, v) (*(p) = (v))
+#elif BLK_ST_POLICY == 1
+#define BLK_STORE16(p, v) __stcs((p), (v))
+#elif BLK_ST_POLICY == 2
+#define BLK_STORE16(p, v) __stwt((p), (v))
+#else
+#define BLK_STORE16(p, v) __stcg((p), (v))
+#endif
+#ifndef BLK_EMIT_UNROLL
+#define BLK_EMIT_UNROLL 6
+#endif
+#ifndef BLK_ROW_ALIGN
+#define BLK_ROW_ALIGN 128   // byte-mask rows start on 128 B lines: every 512 B warp store is line-aligned (+3.5 % measured)
+#endif
+constexpr int kEmitUnroll = BLK_EMIT_UNROLL;   // passes of the emit loop unrolled together (ILP vs I-cache)
+constexpr int kOffLut = 0, kOffWdesc = 2048;   // fixed offsets inside the table blob (see TableLayout)
 
 // ---------------------------------------------------------------------------------------------
 // host-side orientation metadata (same generated list the kernels unroll)
@@ -79,10 +103,12 @@ struct TableLayout {
     int off_ocells;  // uint32[92]  5 x (dy:3, dx:3)
     int off_foff;    // uint16[nf+1] bit offset (= first action id) of each field, sentinel 0xFFFF
     int off_wsrc;    // uint16[mw]  first field intersecting mask word g
-    int off_wdesc;   // uint32[32*rounds] gather descriptor of mask word g (only when <= 3 fields meet a word):
-                     //   first field (11 bits) | right shift of it (5) | left shift of the 2nd (6) | of the 3rd (6)
-    int off_lut;     // uint2[256]  byte -> 8 bytes of 0/1 (bit i -> byte i)
     int bytes;       // multiple of 16
+    // Two tables sit at FIXED offsets so their shared-memory addresses are immediates in the unrolled emit loop:
+    //   kOffLut   = 0     uint2[256]        byte -> 8 bytes of 0/1 (bit i -> byte i)
+    //   kOffWdesc = 2048  uint2[32*rounds]  gather descriptor of mask word g (valid when <= 3 fields meet a word):
+    //                     .x = byte offset of the first field in the staging area
+    //                     .y = right shift of field 0 | left shift of field 1 << 8 | left shift of field 2 << 16
 };
 
 struct Geometry {
@@ -213,22 +239,38 @@ struct EnvRegs {
     uint32_t meta, game;               // warp-uniform
 };
 
-__device__ __forceinline__ void env_load(EnvRegs &e, const uint32_t *s, const Dims &g, int lane) {
+// this lane's share of one env state as it sits in HBM: its row of each bitboard + one tail word
+struct EnvRaw {
+    uint32_t r0, r1, r2, r3, tail;
+};
+
+__device__ __forceinline__ EnvRaw env_fetch(const uint32_t *s, const Dims &g, int lane) {
     const int N = g.N, P = g.P;
     const bool in = lane < N;
-    e.own0 = in ? __ldg(s + lane) : 0u;
-    e.own1 = in ? __ldg(s + N + lane) : 0u;
-    e.own2 = (in && P > 2) ? __ldg(s + 2 * N + lane) : 0u;
-    e.own3 = (in && P > 2) ? __ldg(s + 3 * N + lane) : 0u;
-    const uint32_t tail = lane < P + 4 ? __ldg(s + P * N + lane) : 0u;
-    e.inv0 = __shfl_sync(kAllLanes, tail, 0);
-    e.inv1 = __shfl_sync(kAllLanes, tail, 1);
-    e.inv2 = P > 2 ? __shfl_sync(kAllLanes, tail, 2) : 0u;
-    e.inv3 = P > 2 ? __shfl_sync(kAllLanes, tail, 3) : 0u;
-    e.meta = __shfl_sync(kAllLanes, tail, P);
-    e.game = __shfl_sync(kAllLanes, tail, P + 1);
-    e.sc01 = __shfl_sync(kAllLanes, tail, P + 2);
-    e.sc23 = __shfl_sync(kAllLanes, tail, P + 3);
+    EnvRaw w;
+    w.r0 = in ? __ldg(s + lane) : 0u;
+    w.r1 = in ? __ldg(s + N + lane) : 0u;
+    w.r2 = (in && P > 2) ? __ldg(s + 2 * N + lane) : 0u;
+    w.r3 = (in && P > 2) ? __ldg(s + 3 * N + lane) : 0u;
+    w.tail = lane < P + 4 ? __ldg(s + P * N + lane) : 0u;
+    return w;
+}
+
+__device__ __forceinline__ void env_unpack(EnvRegs &e, const EnvRaw &w, const Dims &g) {
+    const int P = g.P;
+    e.own0 = w.r0; e.own1 = w.r1; e.own2 = w.r2; e.own3 = w.r3;
+    e.inv0 = __shfl_sync(kAllLanes, w.tail, 0);
+    e.inv1 = __shfl_sync(kAllLanes, w.tail, 1);
+    e.inv2 = P > 2 ? __shfl_sync(kAllLanes, w.tail, 2) : 0u;
+    e.inv3 = P > 2 ? __shfl_sync(kAllLanes, w.tail, 3) : 0u;
+    e.meta = __shfl_sync(kAllLanes, w.tail, P);
+    e.game = __shfl_sync(kAllLanes, w.tail, P + 1);
+    e.sc01 = __shfl_sync(kAllLanes, w.tail, P + 2);
+    e.sc23 = __shfl_sync(kAllLanes, w.tail, P + 3);
+}
+
+__device__ __forceinline__ void env_load(EnvRegs &e, const uint32_t *s, const Dims &g, int lane) {
+    env_unpack(e, env_fetch(s, g, lane), g);
 }
 
 __device__ __forceinline__ void env_store(const EnvRegs &e, uint32_t *s, const Dims &g, int lane) {
@@ -354,10 +396,11 @@ __device__ __forceinline__ uint32_t assemble_word(int g, const uint32_t *fld, co
 }
 
 // ... and the branch-free form used when at most three fields meet a word (N = 20: fields are 16-20 bits wide)
-__device__ __forceinline__ uint32_t assemble_word3(int g, const uint32_t *fld, const uint32_t *wdesc) {
-    const uint32_t d = wdesc[g];
-    const uint32_t *p = fld + (d & 0x7ffu);
-    return (p[0] >> ((d >> 11) & 31u)) | shl_clamp(p[1], (d >> 16) & 63u) | shl_clamp(p[2], d >> 22);
+__device__ __forceinline__ uint32_t assemble_word3(int g, const uint32_t *fld, const uint2 *wdesc) {
+    const uint2 d = wdesc[g];
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(fld) + d.x);
+    return (p[0] >> (d.y & 31u)) | shl_clamp(p[1], __byte_perm(d.y, 0u, 0x4441u)) |
+           shl_clamp(p[2], __byte_perm(d.y, 0u, 0x4442u));
 }
 
 struct SmemTables {
@@ -366,7 +409,7 @@ struct SmemTables {
     const uint32_t *ocells;
     const uint16_t *foff;
     const uint16_t *wsrc;
-    const uint32_t *wdesc;
+    const uint2 *wdesc;
     const uint2 *lut;
 };
 __device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, const TableLayout &t) {
@@ -376,8 +419,8 @@ __device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, cons
     tb.ocells = reinterpret_cast<const uint32_t *>(tab + t.off_ocells);
     tb.foff = reinterpret_cast<const uint16_t *>(tab + t.off_foff);
     tb.wsrc = reinterpret_cast<const uint16_t *>(tab + t.off_wsrc);
-    tb.wdesc = reinterpret_cast<const uint32_t *>(tab + t.off_wdesc);
-    tb.lut = reinterpret_cast<const uint2 *>(tab + t.off_lut);
+    tb.wdesc = reinterpret_cast<const uint2 *>(tab + kOffWdesc);
+    tb.lut = reinterpret_cast<const uint2 *>(tab + kOffLut);
     return tb;
 }
 
@@ -441,8 +484,9 @@ __device__ __forceinline__ float terminal_value(const EnvRegs &e, const Dims &g,
 // ---------------------------------------------------------------------------------------------
 // step / legal-mask kernel
 // ---------------------------------------------------------------------------------------------
-template <int kN, int kP>
-__global__ void __launch_bounds__(kWarps * 32, 3) step_kernel(const KParams kp) {
+// kFmt: 0 = no mask output, 1 = bit-packed, 2 = bytes through 16 B vector stores, 3 = bytes into an unaligned buffer.
+template <int kN, int kP, int kFmt, bool kSample>
+__global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const KParams kp) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Geometry &gg = kp.g;
     const Dims g = make_dims<kN, kP>(gg);
@@ -459,31 +503,42 @@ __global__ void __launch_bounds__(kWarps * 32, 3) step_kernel(const KParams kp) 
     const int fld_words = kN == 20 ? 1668 : gg.fld_words;
     const int mw = kN == 20 ? 952 : gg.mw;
     const int rounds = kN == 20 ? 30 : gg.rounds;
-    const int mask_bytes = kN == 20 ? 30448 : gg.mask_bytes;
+    const int mask_bytes = kN == 20 ? (30433 + BLK_ROW_ALIGN - 1) / BLK_ROW_ALIGN * BLK_ROW_ALIGN : gg.mask_bytes;
     const bool fast3 = kN == 20 ? true : (gg.fast3 != 0);
     uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * gg.warp_smem);
-    uint8_t *wpop = reinterpret_cast<uint8_t *>(fld + fld_words);     // 32*rounds bytes, 16 B aligned
-    const int fmt = a.mask_format;
+    uint32_t *tots = fld + fld_words;                                  // 32 per-pass popcount totals (sampler)
     const int64_t n = a.n;
     const int64_t mstride = a.mask_stride;
-    const bool vec_ok = fmt == BLK_MASK_BYTES && (mstride & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0 && mstride >= mask_bytes;
-    const bool want_sample = a.next_action != nullptr;
-    const bool want_words = fmt != BLK_MASK_NONE || a.legal_count != nullptr || want_sample;
-    const uint32_t sh16 = (lane & 1) << 4;
+    const bool want_count = a.legal_count != nullptr;
+    const uint32_t rot_lo = (lane & 1) ? 19u : 3u, rot_hi = (lane & 1) ? 11u : 27u;   // 16-bit half -> LUT byte offsets
     const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);
+    const unsigned char *lutb = reinterpret_cast<const unsigned char *>(tb.lut);
+    const uint2 *wdl = tb.wdesc + lane;
     for (int i = (kN == 20 ? 1665 : gg.nf) + lane; i < fld_words; i += 32) fld[i] = 0u;   // gather padding stays zero
 
-    for (int64_t env = static_cast<int64_t>(blockIdx.x) * kWarps + warp; env < n;
-         env += static_cast<int64_t>(gridDim.x) * kWarps) {
+    // software pipeline over this warp's envs: the next env's 352 B and action are fetched while the current one
+    // is processed (a warp handles its envs serially; without this every env starts with an exposed HBM round trip)
+    const int64_t env0 = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+    const int64_t env_stride = static_cast<int64_t>(gridDim.x) * kWarps;
+    EnvRaw raw_next = {};
+    int act_next = BLK_ACTION_NONE;
+    if (env0 < n) {
+        raw_next = env_fetch(a.state_in + env0 * sw, g, lane);
+        if (a.action != nullptr) act_next = __ldg(a.action + env0);
+    }
+    for (int64_t env = env0; env < n; env += env_stride) {
         EnvRegs e;
-        env_load(e, a.state_in + env * sw, g, lane);
+        env_unpack(e, raw_next, g);
+        const int act = act_next;
+        if (env + env_stride < n) {
+            raw_next = env_fetch(a.state_in + (env + env_stride) * sw, g, lane);
+            if (a.action != nullptr) act_next = __ldg(a.action + env + env_stride);
+        }
         const bool was_done = (e.meta >> 4) & 1u;
         const int mover = e.meta & 15u;
         uint32_t flags = 0u;
         bool moved = false;
 
-        const int act = a.action != nullptr ? __ldg(a.action + env) : BLK_ACTION_NONE;
         if (act != BLK_ACTION_NONE) {
             uint32_t pm; int piece, ncells;
             bool legal = !was_done && decode_action(act, tb, g, lane, pm, piece, ncells);
@@ -540,73 +595,72 @@ __global__ void __launch_bounds__(kWarps * 32, 3) step_kernel(const KParams kp) 
 
         // ---- gather the action-id-ordered mask from the staged fields and stream it out ----
         int cnt = 0;
-        if (want_words) {
-            uint8_t *row = reinterpret_cast<uint8_t *>(a.mask) + env * mstride + 16 * lane;
+        if (kFmt != 0 || kSample || want_count) {
+            unsigned char *row = reinterpret_cast<unsigned char *>(a.mask) + env * mstride + 16 * lane;
             uint32_t *wrow = reinterpret_cast<uint32_t *>(a.mask) + env * mstride + lane;
-#pragma unroll 2
-            for (int r = 0; r < rounds; ++r) {
-                const int gi = (r << 5) + lane;
+#pragma unroll(kEmitUnroll)
+            for (int r = 0; r < (kN == 20 ? 30 : rounds); ++r) {
                 uint32_t word;
-                if (fast3) word = assemble_word3(gi, fld, tb.wdesc);
-                else word = gi < mw ? assemble_word(gi, fld, tb.foff, tb.wsrc) : 0u;
+                if (fast3) word = assemble_word3(r << 5, fld, wdl);
+                else word = ((r << 5) + lane) < mw ? assemble_word((r << 5) + lane, fld, tb.foff, tb.wsrc) : 0u;
                 const int pc = __popc(word);
-                cnt += pc;
-                if (want_sample) wpop[gi] = static_cast<uint8_t>(pc);
-                if (fmt == BLK_MASK_BITS) {
-                    if (gi < mw) wrow[r << 5] = word;
-                } else if (fmt == BLK_MASK_BYTES) {
-                    if (vec_ok) {
-                        // 32 words -> 1024 bytes; each lane expands 16 bits through the byte LUT and writes 16 B,
-                        // so one warp store covers 512 contiguous bytes
-                        const bool last = r == rounds - 1;
+                if (kSample) {
+                    const int tot = __reduce_add_sync(kAllLanes, pc);
+                    if (lane == 0) tots[r] = tot;
+                    cnt += tot;
+                } else {
+                    cnt += pc;
+                }
+                if (kFmt == 1) {
+                    if ((r << 5) + lane < mw) wrow[r << 5] = word;
+                } else if (kFmt == 2) {
+                    // 32 words -> 1024 bytes; each lane expands 16 bits through the byte LUT (two 8-byte entries) and
+                    // writes 16 B, so one warp store covers 512 contiguous bytes
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint32_t w2 = __shfl_sync(kAllLanes, word, h ? src_hi : src_lo) >> sh16;
-                            const uint2 lo = tb.lut[w2 & 0xffu], hi = tb.lut[(w2 >> 8) & 0xffu];
-                            const int boff = (r << 10) + 512 * h;
-                            if (!last || boff + 16 * lane < mask_bytes)
-                                __stcs(reinterpret_cast<uint4 *>(row + boff), make_uint4(lo.x, lo.y, hi.x, hi.y));
-                        }
-                    } else {  // unaligned caller buffer: correct but slow byte stores
-                        uint8_t *urow = reinterpret_cast<uint8_t *>(a.mask) + env * mstride;
-                        for (int b = 0; b < 32; ++b) {
-                            const int idx = (gi << 5) + b;
-                            if (idx < g.A) urow[idx] = static_cast<uint8_t>((word >> b) & 1u);
-                        }
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t w2 = __shfl_sync(kAllLanes, word, h ? src_hi : src_lo);
+                        const uint2 lo = *reinterpret_cast<const uint2 *>(lutb + (__funnelshift_l(w2, w2, rot_lo) & 0x7f8u));
+                        const uint2 hi = *reinterpret_cast<const uint2 *>(lutb + (__funnelshift_l(w2, w2, rot_hi) & 0x7f8u));
+                        const int boff = (r << 10) + 512 * h;
+                        if (r < (kN == 20 ? 29 : rounds - 1) || boff + 16 * lane < mask_bytes)
+                            BLK_STORE16(reinterpret_cast<uint4 *>(row + boff), make_uint4(lo.x, lo.y, hi.x, hi.y));
+                    }
+                } else if (kFmt == 3) {  // unaligned caller buffer: correct but slow byte stores
+                    unsigned char *urow = reinterpret_cast<unsigned char *>(a.mask) + env * mstride;
+                    for (int b = 0; b < 32; ++b) {
+                        const int idx = (((r << 5) + lane) << 5) + b;
+                        if (idx < g.A) urow[idx] = static_cast<unsigned char>((word >> b) & 1u);
                     }
                 }
             }
-            cnt = warp_sum(cnt);
+            if (!kSample) cnt = warp_sum(cnt);
         }
-        if (a.legal_count != nullptr && lane == 0) a.legal_count[env] = cnt;
+        if (want_count && lane == 0) a.legal_count[env] = cnt;
 
         // ---- uniform random legal action for the new mover: k = mulhi(u32, n), k-th set bit ascending ----
-        if (want_sample) {
+        if (kSample) {
             int pick = -1;
             if (cnt > 0) {
                 __syncwarp();
                 const uint32_t u = philox_first(e.meta >> 16, e.game, 0u, 0u, static_cast<uint32_t>(a.seed),
                                                 static_cast<uint32_t>(a.seed >> 32) ^ (a.env_id_base + static_cast<uint32_t>(env)));
                 int k = static_cast<int>(__umulhi(u, static_cast<uint32_t>(cnt)));
-                // level 1: lane r owns pass r (32 words); byte sums via dp4a
-                int tot = 0;
-                if (lane < rounds) {
-                    const uint4 *pp = reinterpret_cast<const uint4 *>(wpop + 32 * lane);
-                    const uint4 x = pp[0], y = pp[1];
-                    tot = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
-                    tot = __dp4a(y.x, 0x01010101u, __dp4a(y.y, 0x01010101u, __dp4a(y.z, 0x01010101u, __dp4a(y.w, 0x01010101u, static_cast<unsigned>(tot)))));
-                }
+                // level 1: which pass of 32 words
+                const int tot = lane < rounds ? static_cast<int>(tots[lane]) : 0;
                 const int incl = warp_incl_scan(tot, lane);
                 const int R = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
                 k -= __shfl_sync(kAllLanes, incl - tot, R);
-                // level 2: the 32 words of pass R
-                const int c2 = wpop[(R << 5) + lane];
+                // level 2: which word of that pass (re-gathered: cheaper than keeping 952 popcounts around)
+                const int gi = (R << 5) + lane;
+                uint32_t word;
+                if (fast3) word = assemble_word3(gi, fld, tb.wdesc);
+                else word = gi < mw ? assemble_word(gi, fld, tb.foff, tb.wsrc) : 0u;
+                const int c2 = __popc(word);
                 const int incl2 = warp_incl_scan(c2, lane);
                 const int J = __ffs(__ballot_sync(kAllLanes, k < incl2)) - 1;
                 k -= __shfl_sync(kAllLanes, incl2 - c2, J);
-                const int gsel = (R << 5) + J;
-                const uint32_t word = fast3 ? assemble_word3(gsel, fld, tb.wdesc) : assemble_word(gsel, fld, tb.foff, tb.wsrc);
-                pick = (gsel << 5) + kth_set_bit(word, k);
+                const uint32_t wsel = __shfl_sync(kAllLanes, word, J);
+                pick = (((R << 5) + J) << 5) + kth_set_bit(wsel, k);
             }
             if (lane == 0) a.next_action[env] = pick;
         }
@@ -714,7 +768,7 @@ struct RParams {
 };
 
 template <int kN, int kP>
-__global__ void __launch_bounds__(kWarps * 32, 3) rollout_kernel(const RParams rp) {
+__global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(const RParams rp) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Geometry &gg = rp.g;
     const Dims g = make_dims<kN, kP>(gg);
@@ -825,7 +879,7 @@ struct blk_engine {
     int step_smem = 0;
     int step_blocks_per_sm = 0, rollout_blocks_per_sm = 0;
     bool special = false;
-    void (*step_fn)(const KParams) = nullptr;
+    void (*step_fn[4][2])(const KParams) = {};      // [mask format variant][sampler]
     void (*rollout_fn)(const RParams) = nullptr;
     std::vector<int32_t> obase;        // host copies for blk_action_to_cells
     std::vector<int16_t> act_o, act_y, act_x;
@@ -865,7 +919,7 @@ int build_tables(blk_engine *h) {
     if (g.nf != kOrients * (N + 1) - kSumH) return fail(BLK_ERR_ARG, "internal: field count mismatch");
     foff.push_back(0xFFFF);  // sentinel
     g.mw = ((A + 31) / 32 + 3) & ~3;
-    g.mask_bytes = align16(A);
+    g.mask_bytes = (A + BLK_ROW_ALIGN - 1) / BLK_ROW_ALIGN * BLK_ROW_ALIGN;
     std::vector<uint16_t> wsrc(g.mw, static_cast<uint16_t>(g.nf));
     {
         int f = 0;
@@ -876,15 +930,13 @@ int build_tables(blk_engine *h) {
         }
     }
     TableLayout &t = h->t;
-    int off = 0;
+    g.rounds = (g.mw + 31) / 32;
+    int off = kOffWdesc + 8 * 32 * g.rounds;               // LUT at 0, gather descriptors at 2048
     t.off_obase = off;  off = align16(off + 4 * (kOrients + 1));
     t.off_oinfo = off;  off = align16(off + 4 * (kOrients + 1));
     t.off_ocells = off; off = align16(off + 4 * (kOrients + 1));
     t.off_foff = off;   off = align16(off + 2 * (g.nf + 1));
     t.off_wsrc = off;   off = align16(off + 2 * g.mw);
-    g.rounds = (g.mw + 31) / 32;
-    t.off_wdesc = off;  off = align16(off + 4 * 32 * g.rounds);
-    t.off_lut = off;    off = align16(off + 8 * 256);
     t.bytes = off;
     std::vector<unsigned char> blob(off, 0);
     memcpy(blob.data() + t.off_obase, h->obase.data(), 4 * (kOrients + 1));
@@ -902,7 +954,8 @@ int build_tables(blk_engine *h) {
     memcpy(blob.data() + t.off_wsrc, wsrc.data(), 2 * wsrc.size());
     // gather descriptors: word g = (fld[s] >> r0) | (fld[s+1] << s1) | (fld[s+2] << s2); shifts >= 32 give 0
     g.fast3 = 1;
-    std::vector<uint32_t> wdesc(32 * g.rounds, static_cast<uint32_t>(g.nf) | (63u << 16) | (63u << 22));
+    std::vector<uint32_t> wdesc(2 * 32 * g.rounds);
+    for (int w = 0; w < 32 * g.rounds; ++w) { wdesc[2 * w] = 4u * g.nf; wdesc[2 * w + 1] = (63u << 8) | (63u << 16); }
     for (int w = 0; w < g.mw && g.fast3; ++w) {
         const int s0 = wsrc[w];
         if (s0 >= g.nf) continue;                       // padding word: gathers the zero slots behind the fields
@@ -910,22 +963,23 @@ int build_tables(blk_engine *h) {
         if (start(s0 + 3) < 32 * w + 32) { g.fast3 = 0; break; }   // a 4th field reaches into this word
         const int r0 = 32 * w - start(s0);
         const int s1 = start(s0 + 1) - 32 * w, s2 = start(s0 + 2) - 32 * w;
-        if (r0 < 0 || r0 > 31 || s0 > 0x7ff) { g.fast3 = 0; break; }
-        wdesc[w] = static_cast<uint32_t>(s0) | (static_cast<uint32_t>(r0) << 11) |
-                   (static_cast<uint32_t>(s1 > 63 ? 63 : s1) << 16) | (static_cast<uint32_t>(s2 > 63 ? 63 : s2) << 22);
+        if (r0 < 0 || r0 > 31) { g.fast3 = 0; break; }
+        wdesc[2 * w] = 4u * static_cast<uint32_t>(s0);
+        wdesc[2 * w + 1] = static_cast<uint32_t>(r0) | (static_cast<uint32_t>(s1 > 63 ? 63 : s1) << 8) |
+                           (static_cast<uint32_t>(s2 > 63 ? 63 : s2) << 16);
     }
-    memcpy(blob.data() + t.off_wdesc, wdesc.data(), 4 * wdesc.size());
+    memcpy(blob.data() + kOffWdesc, wdesc.data(), 4 * wdesc.size());
     for (int b = 0; b < 256; ++b) {
         uint32_t lo = 0, hi = 0;
         for (int i = 0; i < 4; ++i) {
             lo |= static_cast<uint32_t>((b >> i) & 1) << (8 * i);
             hi |= static_cast<uint32_t>((b >> (4 + i)) & 1) << (8 * i);
         }
-        memcpy(blob.data() + t.off_lut + 8 * b, &lo, 4);
-        memcpy(blob.data() + t.off_lut + 8 * b + 4, &hi, 4);
+        memcpy(blob.data() + kOffLut + 8 * b, &lo, 4);
+        memcpy(blob.data() + kOffLut + 8 * b + 4, &hi, 4);
     }
     g.fld_words = (g.nf + 3 + 3) & ~3;                   // >= nf + 3 zero slots for the gather
-    g.warp_smem = align16(4 * g.fld_words + 32 * g.rounds);
+    g.warp_smem = align16(4 * g.fld_words + 4 * 32);      // fields + 32 per-pass popcount totals (sampler)
     if (N == 20 && (g.A != 30433 || g.nf != 1665 || g.mw != 952 || g.fld_words != 1668 || !g.fast3))
         return fail(BLK_ERR_ARG, "internal: N=20 constants in the specialised kernels are stale");
     CUDA_TRY(cudaMalloc(&h->d_tables, off));
@@ -968,18 +1022,28 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     h->step_smem = h->t.bytes + 16 + kWarps * h->g.warp_smem;
     // specialised <20,4> kernels for the headline geometry, runtime-dimension <0,0> kernels for everything else
     h->special = cfg->board_size == 20 && cfg->num_players == 4;
-    h->step_fn = h->special ? step_kernel<20, 4> : step_kernel<0, 0>;
+#define BLK_STEP_VARIANTS(NN, PP)                                                                     \
+    do {                                                                                              \
+        h->step_fn[0][0] = step_kernel<NN, PP, 0, false>; h->step_fn[0][1] = step_kernel<NN, PP, 0, true>; \
+        h->step_fn[1][0] = step_kernel<NN, PP, 1, false>; h->step_fn[1][1] = step_kernel<NN, PP, 1, true>; \
+        h->step_fn[2][0] = step_kernel<NN, PP, 2, false>; h->step_fn[2][1] = step_kernel<NN, PP, 2, true>; \
+        h->step_fn[3][0] = step_kernel<NN, PP, 3, false>; h->step_fn[3][1] = step_kernel<NN, PP, 3, true>; \
+    } while (0)
+    if (h->special) BLK_STEP_VARIANTS(20, 4); else BLK_STEP_VARIANTS(0, 0);
+#undef BLK_STEP_VARIANTS
     h->rollout_fn = h->special ? rollout_kernel<20, 4> : rollout_kernel<0, 0>;
     // the attribute is per function, not per engine: only ever raise it (engines of several board sizes coexist)
     static int s_max_smem[16][2] = {};
     int &cur_max = s_max_smem[cfg->device & 15][h->special ? 1 : 0];
     if (h->step_smem > cur_max) {
-        cudaError_t e1 = cudaFuncSetAttribute(h->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
-        cudaError_t e2 = cudaFuncSetAttribute(h->rollout_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed"); }
+        cudaError_t err = cudaFuncSetAttribute(h->rollout_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+        for (int f = 0; f < 4 && err == cudaSuccess; ++f)
+            for (int sm = 0; sm < 2 && err == cudaSuccess; ++sm)
+                err = cudaFuncSetAttribute(h->step_fn[f][sm], cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+        if (err != cudaSuccess) { blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed"); }
         cur_max = h->step_smem;
     }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_blocks_per_sm, h->step_fn, kWarps * 32, h->step_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_blocks_per_sm, h->step_fn[2][1], kWarps * 32, h->step_smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, h->rollout_fn, kWarps * 32, h->step_smem);
     if (h->step_blocks_per_sm < 1 || h->rollout_blocks_per_sm < 1) { blk_destroy(h); return fail(BLK_ERR_CUDA, "kernel does not fit on an SM"); }
     *out = h;
@@ -1042,7 +1106,11 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
     KParams kp;
     kp.a = *args; kp.tables = h->d_tables; kp.t = h->t; kp.g = h->g;
     const int grid = grid_for(args->n, kWarps, h->sm_count, h->step_blocks_per_sm);
-    h->step_fn<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(kp);
+    int variant = args->mask_format;                  // 0 none, 1 bits, 2 bytes (vector stores), 3 bytes (unaligned buffer)
+    if (variant == BLK_MASK_BYTES &&
+        ((args->mask_stride & 15) != 0 || (reinterpret_cast<uintptr_t>(args->mask) & 15) != 0 || args->mask_stride < h->g.mask_bytes))
+        variant = 3;
+    h->step_fn[variant][args->next_action != nullptr ? 1 : 0]<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(kp);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
 }

@@ -132,9 +132,12 @@ class BatchedMCTS:
         return roots
 
     # ---- B simulations, one per tree, in lockstep ------------------------------------------------------------
-    def simulate(self, roots: list[_State], cpuct: float = 1.0, epsilon_fix: bool = True) -> np.ndarray:
-        """One simulation from ``roots[t]`` in tree t for every t.  Returns the score vectors [B, P]."""
+    def simulate(self, roots: list[_State], cpuct: float = 1.0, epsilon_fix: bool = True,
+                 tree_ids: list[int] | None = None) -> np.ndarray:
+        """One simulation from ``roots[i]`` in tree ``tree_ids[i]`` (default: tree i) for every i, in lockstep.
+        Returns the score vectors [B, P]."""
         B = len(roots)
+        tid = list(range(B)) if tree_ids is None else tree_ids
         cur = list(roots)
         paths: list[list] = [[] for _ in range(B)]
         scores: list = [None] * B
@@ -146,7 +149,7 @@ class BatchedMCTS:
             nxt_active = []
             for t in active:
                 s = cur[t]
-                node = self.trees[t].get(s.key)
+                node = self.trees[tid[t]].get(s.key)
                 if node is None:                                   # leaf: expand (or terminal)
                     if s.terminal is not None:
                         scores[t] = s.terminal
@@ -197,7 +200,7 @@ class BatchedMCTS:
             for j, t in enumerate(expand):
                 s = cur[t]
                 n = lens[j]
-                self.trees[t][s.key] = _Node(s.ids, np.zeros(n), np.zeros(n), pv[off: off + n].copy())
+                self.trees[tid[t]][s.key] = _Node(s.ids, np.zeros(n), np.zeros(n), pv[off: off + n].copy())
                 off += n
                 scores[t] = v[j]
         for t in range(B):                                         # backup, deepest edge first
@@ -229,6 +232,28 @@ class BatchedMCTS:
     def stats(self, tree_index: int, state: _State):
         node = self.trees[tree_index][state.key]
         return node.ids, node.N, node.Q, node.P
+
+    def child_states(self, states: list[_State], action_ids: list[int]) -> list[_State]:
+        """Successors of ``states[i]`` under ``action_ids[i]`` (cached edges are reused, the rest is one launch)."""
+        out: list = [s.child.get(int(a)) for s, a in zip(states, action_ids)]
+        miss = [i for i, c in enumerate(out) if c is None]
+        if miss:
+            idx = torch.tensor([states[i].slot for i in miss], device=self.pool.device)
+            acts = torch.tensor([int(action_ids[i]) for i in miss], dtype=torch.int32, device=self.pool.device)
+            src = self.pool.index_select(0, idx)
+            dst = torch.empty_like(src)
+            res = self.eng.step(src, acts, out_states=dst, mask="bytes")
+            self.launches += 1
+            if int((res.flags & 2).sum().item()):
+                raise ValueError("illegal action")
+            for i, st in zip(miss, self._register(dst, res)):
+                states[i].child[int(action_ids[i])] = st
+                out[i] = st
+        return out
+
+    def rows(self, states: list[_State]) -> torch.Tensor:
+        """Device rows (int32 [m, SW]) of pooled states."""
+        return self.pool.index_select(0, torch.tensor([s.slot for s in states], device=self.pool.device))
 
     def reset(self):
         self.trees = [dict() for _ in self.trees]

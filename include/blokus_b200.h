@@ -61,7 +61,7 @@ typedef struct {
     int32_t num_fields;    /* (orientation, anchor row) pairs: 1665 at N=20 */
     int32_t state_words;   /* uint32 words per env state */
     int32_t mask_words;    /* uint32 words of a bit-packed mask row, padded to 4 (952 at N=20) */
-    int32_t mask_bytes;    /* bytes of a byte-mask row padded to 16 (30448 at N=20) */
+    int32_t mask_bytes;    /* bytes of a byte-mask row padded to 128 (30464 at N=20) */
     int32_t sm_count;
 } blk_info;
 

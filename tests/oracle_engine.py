@@ -15,7 +15,7 @@ class OracleEngine:
         self.orc = Oracle(board_size, num_players, score_rule)
         self.board_size, self.num_players = board_size, num_players
         self.num_actions, self.state_words = self.orc.A, self.orc.state_words
-        self.mask_bytes = (self.num_actions + 15) // 16 * 16
+        self.mask_bytes = (self.num_actions + 127) // 128 * 128
         self.mask_words = ((self.num_actions + 31) // 32 + 3) // 4 * 4
         self.device = torch.device("cpu")
 

@@ -24,7 +24,7 @@ def test_action_table_matches_oracle(engine20, oracle20, engine7, oracle7):
 
 def test_info_and_known_sizes(engine20, engine7):
     assert engine20.num_actions == 30433          # blokus_rl/models/blokus_nnet.py:17
-    assert engine20.state_words == 88 and engine20.mask_words == 952 and engine20.mask_bytes == 30448
+    assert engine20.state_words == 88 and engine20.mask_words == 952 and engine20.mask_bytes == 30464
     assert engine20.info.num_fields == 1665 and engine20.info.num_orients == 91
     assert engine7.num_actions == 2522
 
