@@ -103,6 +103,8 @@ struct TableLayout {
     int off_ocells;  // uint32[92]  5 x (dy:3, dx:3)
     int off_foff;    // uint16[nf+1] bit offset (= first action id) of each field, sentinel 0xFFFF
     int off_wsrc;    // uint16[mw]  first field intersecting mask word g
+    int off_fbase;   // uint16[92]  first field index of each orientation
+    int off_f2o;     // uint8[nf]   orientation of each field
     int bytes;       // multiple of 16
     // Two tables sit at FIXED offsets so their shared-memory addresses are immediates in the unrolled emit loop:
     //   kOffLut   = 0     uint2[256]        byte -> 8 bytes of 0/1 (bit i -> byte i)
@@ -168,8 +170,7 @@ __device__ __forceinline__ uint32_t sel4(uint32_t a0, uint32_t a1, uint32_t a2, 
 }
 
 // Philox-4x32-10 (Salmon et al. SC'11); identical to oracle/blokus_oracle.c:orc_philox.
-__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                                 uint32_t k1) {
+__device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -178,7 +179,13 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
         c0 = n0; c1 = l1; c2 = n2; c3 = l0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    return c0;
+    return make_uint4(c0, c1, c2, c3);
+}
+// The sampler's draw for a state at `ply`: one Philox block serves four consecutive plies
+// (counter = (ply >> 2, game, stream, 0), word ply & 3), so a rollout recomputes it every fourth ply only.
+__device__ __forceinline__ uint32_t philox_word(const uint4 &b, uint32_t ply) {
+    const uint32_t i = ply & 3u;
+    return i == 0 ? b.x : (i == 1 ? b.y : (i == 2 ? b.z : b.w));
 }
 
 // k-th (0-based) set bit of w; requires popc(w) > k.  (__fns is emulated with ~500 instructions.)
@@ -409,6 +416,8 @@ struct SmemTables {
     const uint32_t *ocells;
     const uint16_t *foff;
     const uint16_t *wsrc;
+    const uint16_t *fbase;
+    const uint8_t *f2o;
     const uint2 *wdesc;
     const uint2 *lut;
 };
@@ -419,6 +428,8 @@ __device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, cons
     tb.ocells = reinterpret_cast<const uint32_t *>(tab + t.off_ocells);
     tb.foff = reinterpret_cast<const uint16_t *>(tab + t.off_foff);
     tb.wsrc = reinterpret_cast<const uint16_t *>(tab + t.off_wsrc);
+    tb.fbase = reinterpret_cast<const uint16_t *>(tab + t.off_fbase);
+    tb.f2o = tab + t.off_f2o;
     tb.wdesc = reinterpret_cast<const uint2 *>(tab + kOffWdesc);
     tb.lut = reinterpret_cast<const uint2 *>(tab + kOffLut);
     return tb;
@@ -452,6 +463,22 @@ __device__ __forceinline__ bool decode_action(int act, const SmemTables &tb, con
         if (c < ncells && ay + dy == lane) pm |= 1u << (ax + dx);
     }
     return true;
+}
+
+// the same from a (field, bit) pair, as the rollout sampler finds it: no search, no division
+__device__ __forceinline__ void decode_field(int fsel, int bit, const SmemTables &tb, int lane, uint32_t &pm,
+                                             int &piece, int &ncells) {
+    const int o = tb.f2o[fsel];
+    const int ay = fsel - static_cast<int>(tb.fbase[o]);
+    const uint32_t oi = tb.oinfo[o], cells = tb.ocells[o];
+    piece = oi & 31;
+    ncells = (oi >> 16) & 15;
+    pm = 0u;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const int dy = (cells >> (6 * c)) & 7, dx = (cells >> (6 * c + 3)) & 7;
+        if (c < ncells && ay + dy == lane) pm |= 1u << (bit + dx);
+    }
 }
 
 __device__ __forceinline__ void apply_placement(EnvRegs &e, int p, uint32_t pm, int piece, int ncells) {
@@ -642,8 +669,9 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
             int pick = -1;
             if (cnt > 0) {
                 __syncwarp();
-                const uint32_t u = philox_first(e.meta >> 16, e.game, 0u, 0u, static_cast<uint32_t>(a.seed),
-                                                static_cast<uint32_t>(a.seed >> 32) ^ (a.env_id_base + static_cast<uint32_t>(env)));
+                const uint32_t ply = e.meta >> 16;
+                const uint32_t u = philox_word(philox4(ply >> 2, e.game, 0u, 0u, static_cast<uint32_t>(a.seed),
+                                                       static_cast<uint32_t>(a.seed >> 32) ^ (a.env_id_base + static_cast<uint32_t>(env))), ply);
                 int k = static_cast<int>(__umulhi(u, static_cast<uint32_t>(cnt)));
                 // level 1: which pass of 32 words
                 const int tot = lane < rounds ? static_cast<int>(tots[lane]) : 0;
@@ -795,6 +823,8 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(co
         const uint32_t key0 = static_cast<uint32_t>(a.seed);
         const uint32_t key1 = static_cast<uint32_t>(a.seed >> 32) ^ (a.rollout_id_base + static_cast<uint32_t>(gid));
         int nply = 0;
+        uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+        int rnd_block = -1;
         bool over = (e.meta >> 4) & 1u;
         // the root's mover is evaluated first; afterwards every player gets a try after each placement (R8)
         int cand = static_cast<int>(e.meta & 15u);
@@ -816,34 +846,50 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(co
             e.meta = (e.meta & ~15u) | static_cast<uint32_t>(cand);
             // count legal actions: lane sums popcounts over its contiguous chunk of fields (field order = id order)
             int mine = 0;
-            for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
+            if (kN == 20) {                     // 1665 fields = 32 x 52 (+1 for lane 31): 13 conflict-free LDS.128 per lane
+                const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 13 * lane;
+#pragma unroll
+                for (int j = 0; j < 13; ++j) {
+                    const uint4 x = f4[j];
+                    mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+                }
+                if (lane == 31) mine += __popc(fld[1664]);
+            } else {
+                for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
+            }
             const int incl = warp_incl_scan(mine, lane);
             const int cnt = __shfl_sync(kAllLanes, incl, 31);
-            const uint32_t u = philox_first(e.meta >> 16, e.game, 1u, 0u, key0, key1);
-            int k = static_cast<int>(__umulhi(u, static_cast<uint32_t>(cnt)));
+            const uint32_t ply = e.meta >> 16;
+            if (static_cast<int>(ply >> 2) != rnd_block) {
+                rnd = philox4(ply >> 2, e.game, 1u, 0u, key0, key1);
+                rnd_block = static_cast<int>(ply >> 2);
+            }
+            int k = static_cast<int>(__umulhi(philox_word(rnd, ply), static_cast<uint32_t>(cnt)));
             const int L = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
             k -= __shfl_sync(kAllLanes, incl - mine, L);
-            // second level: the chunk of lane L, up to `per` (<= 64) fields, 32 at a time
+            // second level: the chunk of lane L, 32 fields at a time
+            const int chunk = kN == 20 ? 52 : per;
+            const int chunk_len = kN == 20 ? (L == 31 ? 53 : 52) : per;
             int fsel = -1, kk = 0;
-            for (int half = 0; half * 32 < per; ++half) {
+            for (int half = 0; half * 32 < chunk_len; ++half) {
                 const int j = half * 32 + lane;
-                const int i = L * per + j;
-                const int c = (j < per && i < nf) ? __popc(fld[i]) : 0;
+                const int i = L * chunk + j;
+                const int c = (j < chunk_len && i < nf) ? __popc(fld[i]) : 0;
                 const int inc2 = warp_incl_scan(c, lane);
                 const uint32_t b = __ballot_sync(kAllLanes, k < inc2);
                 if (b) {
                     const int J = __ffs(b) - 1;
                     kk = k - __shfl_sync(kAllLanes, inc2 - c, J);
-                    fsel = L * per + half * 32 + J;
+                    fsel = L * chunk + half * 32 + J;
                     break;
                 }
                 k -= __shfl_sync(kAllLanes, inc2, 31);
             }
-            const int act = static_cast<int>(tb.foff[fsel]) + kth_set_bit(fld[fsel], kk);
+            const int bit = kth_set_bit(fld[fsel], kk);
             if (a.action_log != nullptr && lane == 0 && nply < a.log_stride - 1)
-                a.action_log[gid * a.log_stride + nply] = static_cast<uint16_t>(act);
+                a.action_log[gid * a.log_stride + nply] = static_cast<uint16_t>(tb.foff[fsel] + bit);
             uint32_t pm; int piece, ncells;
-            decode_action(act, tb, g, lane, pm, piece, ncells);
+            decode_field(fsel, bit, tb, lane, pm, piece, ncells);
             apply_placement(e, cand, pm, piece, ncells);
             ++nply;
             tries = P;
@@ -937,6 +983,8 @@ int build_tables(blk_engine *h) {
     t.off_ocells = off; off = align16(off + 4 * (kOrients + 1));
     t.off_foff = off;   off = align16(off + 2 * (g.nf + 1));
     t.off_wsrc = off;   off = align16(off + 2 * g.mw);
+    t.off_fbase = off;  off = align16(off + 2 * (kOrients + 1));
+    t.off_f2o = off;    off = align16(off + g.nf);
     t.bytes = off;
     std::vector<unsigned char> blob(off, 0);
     memcpy(blob.data() + t.off_obase, h->obase.data(), 4 * (kOrients + 1));
@@ -952,6 +1000,15 @@ int build_tables(blk_engine *h) {
     }
     memcpy(blob.data() + t.off_foff, foff.data(), 2 * foff.size());
     memcpy(blob.data() + t.off_wsrc, wsrc.data(), 2 * wsrc.size());
+    {
+        int f = 0;
+        for (int o = 0; o <= kOrients; ++o) {
+            const uint16_t fb = static_cast<uint16_t>(f);
+            memcpy(blob.data() + t.off_fbase + 2 * o, &fb, 2);
+            if (o == kOrients) break;
+            for (int y = 0; y < N - kOrient[o].h + 1; ++y) blob[t.off_f2o + f++] = static_cast<unsigned char>(o);
+        }
+    }
     // gather descriptors: word g = (fld[s] >> r0) | (fld[s+1] << s1) | (fld[s+2] << s2); shifts >= 32 give 0
     g.fast3 = 1;
     std::vector<uint32_t> wdesc(2 * 32 * g.rounds);

@@ -86,7 +86,7 @@ typedef struct {
     uint8_t *flags;             /* nullable [n]; BLK_FLAG_* */
     int16_t *scores;            /* nullable [n][P]; scores after the step (final rule applied; before auto-reset) */
     int32_t *next_action;       /* nullable [n]; uniform random legal action of the next mover, -1 if none */
-    uint64_t seed;              /* Philox-4x32-10 key = (seed_lo, seed_hi ^ (env_id_base + i)), ctr = (ply, game, 0, 0) */
+    uint64_t seed;              /* Philox-4x32-10 key = (seed_lo, seed_hi ^ (env_id_base + i)), ctr = (ply >> 2, game, 0, 0), word ply & 3 */
     uint32_t env_id_base;       /* global id of env 0 of this batch (multi-GPU sharding keeps results partition-invariant) */
     uint32_t options;           /* BLK_OPT_* */
 } blk_step_args;
@@ -96,7 +96,7 @@ typedef struct {
     int64_t n_roots;
     const uint32_t *roots;      /* [n_roots][state_words] */
     int32_t per_root;           /* playouts per root */
-    uint64_t seed;              /* key = (seed_lo, seed_hi ^ game_index), game_index = rollout_id_base + root*per_root + j; ctr = (ply, 0, 1, 0) */
+    uint64_t seed;              /* key = (seed_lo, seed_hi ^ game_index), game_index = rollout_id_base + root*per_root + j; ctr = (ply >> 2, game, 1, 0), word ply & 3 */
     uint32_t rollout_id_base;
     int16_t *final_scores;      /* [n_roots*per_root][P] */
     uint8_t *winners;           /* nullable [n_roots*per_root] bitmask of winners */

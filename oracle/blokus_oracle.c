@@ -366,7 +366,7 @@ void orc_unpack(const uint32_t *w, orc_state *s) {
     s->game = w[b + g_P + 1];
 }
 
-/* ---- counter-based RNG: Philox-4x32-10 (Salmon et al., SC'11), key=(seed_lo, seed_hi^env), ctr=(ply, game, stream, 0) ---- */
+/* ---- counter-based RNG: Philox-4x32-10 (Salmon et al., SC'11), key=(seed_lo, seed_hi^env), ctr=(ply>>2, game, stream, 0) ---- */
 void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {
     for (int r = 0; r < 10; r++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
@@ -382,8 +382,9 @@ int orc_sample_action(const orc_state *s, uint64_t seed, uint32_t env_id, uint32
     int n = fast ? orc_fast_legal_mask(s, s->mover, scratch_mask) : orc_legal_mask(s, s->mover, scratch_mask);
     if (n == 0) return -1;
     uint32_t r[4];
-    orc_philox(s->ply, s->game, stream, 0, (uint32_t)seed, (uint32_t)(seed >> 32) ^ env_id, r);
-    uint32_t k = (uint32_t)(((uint64_t)r[0] * (uint64_t)(uint32_t)n) >> 32);
+    /* one Philox block serves four consecutive plies: counter (ply >> 2, game, stream, 0), word ply & 3 */
+    orc_philox(s->ply >> 2, s->game, stream, 0, (uint32_t)seed, (uint32_t)(seed >> 32) ^ env_id, r);
+    uint32_t k = (uint32_t)(((uint64_t)r[s->ply & 3] * (uint64_t)(uint32_t)n) >> 32);
     for (int a = 0; a < g_nact; a++) if (scratch_mask[a]) { if (k == 0) return a; k--; }
     return -1;
 }
