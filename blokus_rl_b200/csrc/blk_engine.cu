@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                     cnt += pc;
                 }
                 if (kFmt == 1) {
-                    if ((r << 5) + lane < mw) wrow[r << 5] = word;
+                    if (r < (kN == 20 ? 29 : rounds - 1) || (r << 5) + lane < mw) wrow[r << 5] = word;
                 } else if (kFmt == 2) {
                     // 32 words -> 1024 bytes; each lane expands 16 bits through the byte LUT (two 8-byte entries) and
                     // writes 16 B, so one warp store covers 512 contiguous bytes
