@@ -57,6 +57,7 @@ constexpr uint32_t kAllLanes = 0xffffffffu;
 #ifndef BLK_ROW_ALIGN
 #define BLK_ROW_ALIGN 128   // byte-mask rows start on 128 B lines: every 512 B warp store is line-aligned (+3.5 % measured)
 #endif
+constexpr int kQueueSlots = 64;   // work-queue counters for up to 64 launches of one engine in flight at once
 constexpr int kEmitUnroll = BLK_EMIT_UNROLL;   // passes of the emit loop unrolled together (ILP vs I-cache)
 constexpr int kOffLut = 0, kOffWdesc = 2048;   // fixed offsets inside the table blob (see TableLayout)
 
@@ -127,6 +128,7 @@ struct KParams {
     const unsigned char *tables;
     TableLayout t;
     Geometry g;
+    unsigned long long *queue;   // [0] next env ticket, [1] blocks finished (self-resetting, one slot per launch in flight)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -236,6 +238,22 @@ __device__ __forceinline__ Dims make_dims(const Geometry &g) {
     d.score_rule = g.score_rule;
     d.full = kN ? ((1u << kN) - 1u) : g.full;
     return d;
+}
+
+// Dynamic work distribution: warps draw env indices from a global ticket counter instead of a fixed stride, so
+// nobody idles in the last wave (65,536 envs over 3,552 resident warps is 18.45 each) and uneven envs
+// (skipped players, finished games) even out.  The last block to finish resets the counters for the next launch.
+__device__ __forceinline__ int64_t next_ticket(unsigned long long *queue, int lane) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(queue, 1ULL);
+    return static_cast<int64_t>(__shfl_sync(kAllLanes, t, 0));
+}
+__device__ __forceinline__ void queue_release(unsigned long long *queue) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long done = atomicAdd(queue + 1, 1ULL);
+        if (done == gridDim.x - 1) { queue[0] = 0ULL; queue[1] = 0ULL; }
+    }
 }
 
 // Per-warp view of one env held in registers (lane y = board row y).
@@ -545,22 +563,23 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
 
     // software pipeline over this warp's envs: the next env's 352 B and action are fetched while the current one
     // is processed (a warp handles its envs serially; without this every env starts with an exposed HBM round trip)
-    const int64_t env0 = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
-    const int64_t env_stride = static_cast<int64_t>(gridDim.x) * kWarps;
+    int64_t env = next_ticket(kp.queue, lane);
+    int64_t env_next = next_ticket(kp.queue, lane), env_after = 0;
     EnvRaw raw_next = {};
     int act_next = BLK_ACTION_NONE;
-    if (env0 < n) {
-        raw_next = env_fetch(a.state_in + env0 * sw, g, lane);
-        if (a.action != nullptr) act_next = __ldg(a.action + env0);
+    if (env < n) {
+        raw_next = env_fetch(a.state_in + env * sw, g, lane);
+        if (a.action != nullptr) act_next = __ldg(a.action + env);
     }
-    for (int64_t env = env0; env < n; env += env_stride) {
+    for (; env < n; env = env_next, env_next = env_after) {
         EnvRegs e;
         env_unpack(e, raw_next, g);
         const int act = act_next;
-        if (env + env_stride < n) {
-            raw_next = env_fetch(a.state_in + (env + env_stride) * sw, g, lane);
-            if (a.action != nullptr) act_next = __ldg(a.action + env + env_stride);
+        if (env_next < n) {
+            raw_next = env_fetch(a.state_in + env_next * sw, g, lane);
+            if (a.action != nullptr) act_next = __ldg(a.action + env_next);
         }
+        env_after = next_ticket(kp.queue, lane);
         const bool was_done = (e.meta >> 4) & 1u;
         const int mover = e.meta & 15u;
         uint32_t flags = 0u;
@@ -702,6 +721,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
         if (a.state_out != nullptr) env_store(e, a.state_out + env * sw, g, lane);
         __syncwarp();
     }
+    queue_release(kp.queue);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -793,6 +813,7 @@ struct RParams {
     const unsigned char *tables;
     TableLayout t;
     Geometry g;
+    unsigned long long *queue;
 };
 
 template <int kN, int kP>
@@ -815,8 +836,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(co
     const int64_t total = a.n_roots * a.per_root;
     const int per = (nf + 31) >> 5;   // contiguous fields per lane for the k-th-bit search (53 at N = 20)
 
-    for (int64_t gid = static_cast<int64_t>(blockIdx.x) * kWarps + warp; gid < total;
-         gid += static_cast<int64_t>(gridDim.x) * kWarps) {
+    for (int64_t gid = next_ticket(rp.queue, lane); gid < total; gid = next_ticket(rp.queue, lane)) {
         const int64_t root = gid / a.per_root;
         EnvRegs e;
         env_load(e, a.roots + root * sw, g, lane);
@@ -909,6 +929,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(co
         }
         __syncwarp();
     }
+    queue_release(rp.queue);
 }
 
 }  // namespace
@@ -921,6 +942,8 @@ struct blk_engine {
     Geometry g;
     TableLayout t;
     unsigned char *d_tables = nullptr;
+    unsigned long long *d_queue = nullptr;   // kQueueSlots x {ticket, finished}; launch i uses slot i % kQueueSlots
+    unsigned launch_seq = 0;
     int sm_count = 0;
     int step_smem = 0;
     int step_blocks_per_sm = 0, rollout_blocks_per_sm = 0;
@@ -1041,6 +1064,8 @@ int build_tables(blk_engine *h) {
         return fail(BLK_ERR_ARG, "internal: N=20 constants in the specialised kernels are stale");
     CUDA_TRY(cudaMalloc(&h->d_tables, off));
     CUDA_TRY(cudaMemcpy(h->d_tables, blob.data(), off, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned long long) * 2 * kQueueSlots));
+    CUDA_TRY(cudaMemset(h->d_queue, 0, sizeof(unsigned long long) * 2 * kQueueSlots));
     return BLK_OK;
 }
 
@@ -1110,6 +1135,7 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
 void blk_destroy(blk_engine *h) {
     if (!h) return;
     if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_queue) cudaFree(h->d_queue);
     delete h;
 }
 
@@ -1162,6 +1188,7 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     KParams kp;
     kp.a = *args; kp.tables = h->d_tables; kp.t = h->t; kp.g = h->g;
+    kp.queue = h->d_queue + 2 * (h->launch_seq++ % kQueueSlots);
     const int grid = grid_for(args->n, kWarps, h->sm_count, h->step_blocks_per_sm);
     int variant = args->mask_format;                  // 0 none, 1 bits, 2 bytes (vector stores), 3 bytes (unaligned buffer)
     if (variant == BLK_MASK_BYTES &&
@@ -1217,6 +1244,7 @@ int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream) {
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     RParams rp;
     rp.a = *args; rp.tables = h->d_tables; rp.t = h->t; rp.g = h->g;
+    rp.queue = h->d_queue + 2 * (h->launch_seq++ % kQueueSlots);
     const int grid = grid_for(args->n_roots * args->per_root, kWarps, h->sm_count, h->rollout_blocks_per_sm);
     h->rollout_fn<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(rp);
     CUDA_TRY(cudaGetLastError());
