@@ -1,24 +1,49 @@
-"""In-tree build of libblokus_b200.so (nvcc, sm_100a only)."""
+"""In-tree build of libblokus_b200.so (nvcc, sm_100a only).
+
+One object per kernel specialisation (blk_inst.cu compiled with -DBLK_INST_N/-DBLK_INST_P) plus the host /
+C-ABI object, compiled in parallel and linked into blokus_rl_b200/libblokus_b200.so.
+"""
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
-SRC = PKG / "csrc" / "blk_engine.cu"
-DEPS = [SRC, PKG / "csrc" / "blk_orient.inc", ROOT / "include" / "blokus_b200.h"]
+CSRC = PKG / "csrc"
+OBJ = PKG / "build"
 OUT = PKG / "libblokus_b200.so"
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+DEPS = [CSRC / "blk_engine.cu", CSRC / "blk_inst.cu", CSRC / "blk_kernels.cuh", CSRC / "blk_orient.inc",
+        ROOT / "include" / "blokus_b200.h"]
+GEOMETRIES = [(20, 4), (20, 2), (14, 4), (14, 2), (7, 2), (0, 0)]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None) -> Path:
     if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
         return OUT
-    cmd = ["nvcc", *NVCC_FLAGS, *( ["-Xptxas", "-v"] if verbose else []), "-o", str(OUT), str(SRC)]
-    subprocess.check_call(cmd)
+    OBJ.mkdir(exist_ok=True)
+    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (extra_flags or [])
+    jobs = [(OBJ / "blk_engine.o", ["nvcc", *flags, "-c", str(CSRC / "blk_engine.cu")])]
+    for n, p in GEOMETRIES:
+        jobs.append((OBJ / f"blk_inst_{n}_{p}.o",
+                     ["nvcc", *flags, f"-DBLK_INST_N={n}", f"-DBLK_INST_P={p}", "-c", str(CSRC / "blk_inst.cu")]))
+
+    def run(job):
+        obj, cmd = job
+        res = subprocess.run(cmd + ["-o", str(obj)], capture_output=True, text=True)
+        if verbose:
+            sys.stderr.write(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {obj.name}:\n{res.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(run, jobs))
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(OUT), *map(str, objs)])
     return OUT
 
 

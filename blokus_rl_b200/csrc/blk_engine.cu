@@ -1,65 +1,24 @@
-// blk_engine.cu -- B200 (sm_100a) batched Blokus environment engine: kernels + C ABI.
+// blk_engine.cu -- host side of the B200 (sm_100a) batched Blokus environment engine: tables, launch logic, C ABI,
+// and the small streaming kernels.  The step / rollout kernels live in blk_kernels.cuh (instantiated per geometry
+// by blk_inst.cu).
 //
 // Hot path (reference call sites in blokus_rl/colossumrl/blokus_wrapper.py):
-//   a1 new_state      -> reset_kernel            a2 next_state   -> step_kernel<true>
-//   a3 valid_actions  -> step_kernel<false/true> a4 get_winners  -> step_kernel / ended_kernel
-//   a5 canonical_board-> observe_kernel          a6 board_contents -> contents_kernel
-//   a7 action table   -> build_tables() (host)   rollouts (new)  -> rollout_kernel
-//
-// Mapping: ONE WARP PER ENV.  Lane y holds row y of every player's bitboard (bit x = column x), so
-// the whole board state lives in 4 registers per lane.  Legality is evaluated bit-parallel across
-// the 20 anchor columns: lane = anchor row, `fr[r]`/`dg[r]` are rows lane..lane+4 of the "free and
-// not edge-adjacent to own colour" and "diagonal contact / start corner" boards, and each of the 91
-// piece orientations is 4-5 LOP3s with immediate cell offsets (blk_orient.inc, generated).  The
-// resulting (orientation, anchor-row) *fields* are staged in shared memory, re-assembled into the
-// action-id-ordered bit mask by a table-driven gather (tables staged once per block with a 1-D TMA
-// bulk copy), and streamed to HBM as 128-bit stores (bit-packed or one byte per action).
+//   a1 new_state       -> reset_kernel              a2 next_state     -> step_kernel
+//   a3 valid_actions   -> step_kernel               a4 get_winners    -> step_kernel / ended_kernel
+//   a5 canonical_board -> observe_kernel            a6 board_contents -> contents_kernel
+//   a7 action table    -> build_tables() (host)     rollouts (new)    -> rollout_kernel
 //
 // No tensor cores: nothing here is a contraction.  No CPU fallback: every entry point needs the GPU.
-#include <cuda_runtime.h>
-
-#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "../../include/blokus_b200.h"
+#include "blk_kernels.cuh"
+
+using namespace blk;
 
 namespace {
-
-constexpr int kMaxN = 20;
-constexpr int kPieces = 21;
-constexpr int kOrients = 91;
-constexpr int kSumH = 246;  // sum of bounding-box heights over the 91 orientations
-#ifndef BLK_WARPS
-#define BLK_WARPS 8
-#define BLK_MIN_BLOCKS 3
-#endif
-constexpr int kWarps = BLK_WARPS;   // warps (= envs in flight) per block
-constexpr uint32_t kFullInv = (1u << kPieces) - 1u;
-constexpr uint32_t kAllLanes = 0xffffffffu;
-#ifndef BLK_ST_POLICY
-#define BLK_ST_POLICY 1
-#endif
-#if BLK_ST_POLICY == 0
-#define BLK_STORE16(p, v) (*(p) = (v))
-#elif BLK_ST_POLICY == 1
-#define BLK_STORE16(p, v) __stcs((p), (v))
-#elif BLK_ST_POLICY == 2
-#define BLK_STORE16(p, v) __stwt((p), (v))
-#else
-#define BLK_STORE16(p, v) __stcg((p), (v))
-#endif
-#ifndef BLK_EMIT_UNROLL
-#define BLK_EMIT_UNROLL 6
-#endif
-#ifndef BLK_ROW_ALIGN
-#define BLK_ROW_ALIGN 128   // byte-mask rows start on 128 B lines: every 512 B warp store is line-aligned (+3.5 % measured)
-#endif
-constexpr int kQueueSlots = 64;   // work-queue counters for up to 64 launches of one engine in flight at once
-constexpr int kEmitUnroll = BLK_EMIT_UNROLL;   // passes of the emit loop unrolled together (ILP vs I-cache)
-constexpr int kOffLut = 0, kOffWdesc = 2048;   // fixed offsets inside the table blob (see TableLayout)
 
 // ---------------------------------------------------------------------------------------------
 // host-side orientation metadata (same generated list the kernels unroll)
@@ -96,633 +55,6 @@ int fail(int code, const std::string &msg) {
         if (e_ != cudaSuccess)                                                                      \
             return fail(BLK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
     } while (0)
-
-// Device-resident constant tables, one blob, staged into shared memory by TMA (offsets in bytes).
-struct TableLayout {
-    int off_obase;   // int32[92]   first action id of each orientation (+ sentinel A)
-    int off_oinfo;   // uint32[92]  piece | h<<8 | w<<12 | ncells<<16
-    int off_ocells;  // uint32[92]  5 x (dy:3, dx:3)
-    int off_foff;    // uint16[nf+1] bit offset (= first action id) of each field, sentinel 0xFFFF
-    int off_wsrc;    // uint16[mw]  first field intersecting mask word g
-    int off_fbase;   // uint16[92]  first field index of each orientation
-    int off_f2o;     // uint8[nf]   orientation of each field
-    int bytes;       // multiple of 16
-    // Two tables sit at FIXED offsets so their shared-memory addresses are immediates in the unrolled emit loop:
-    //   kOffLut   = 0     uint2[256]        byte -> 8 bytes of 0/1 (bit i -> byte i)
-    //   kOffWdesc = 2048  uint2[32*rounds]  gather descriptor of mask word g (valid when <= 3 fields meet a word):
-    //                     .x = byte offset of the first field in the staging area
-    //                     .y = right shift of field 0 | left shift of field 1 << 8 | left shift of field 2 << 16
-};
-
-struct Geometry {
-    int N, P, A, nf, mw, mask_bytes, sw, score_rule;
-    uint32_t full;      // (1 << N) - 1
-    int warp_smem;      // bytes of per-warp scratch (fields + per-word popcounts)
-    int fld_words;      // >= nf + 3; words nf..nf+2 stay zero (gather padding)
-    int rounds;         // ceil(mw / 32): warp-wide passes over the mask words
-    int fast3;          // 1 when every mask word gathers from <= 3 fields (true at N = 20)
-};
-
-struct KParams {
-    blk_step_args a;
-    const unsigned char *tables;
-    TableLayout t;
-    Geometry g;
-    unsigned long long *queue;   // [0] next env ticket, [1] blocks finished (self-resetting, one slot per launch in flight)
-};
-
-// ---------------------------------------------------------------------------------------------
-// device helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-// One elected thread issues a 1-D TMA bulk copy global -> shared and every thread waits on the mbarrier.
-__device__ __forceinline__ void tma_load_tables(unsigned char *dst, const unsigned char *src, int bytes,
-                                                uint64_t *bar) {
-    const uint32_t bar_a = smem_u32(bar);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                smem_u32(dst)),
-            "l"(src), "r"(bytes), "r"(bar_a)
-            : "memory");
-    }
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar_a)
-            : "memory");
-    }
-}
-
-__device__ __forceinline__ uint32_t sel4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int q) {
-    return q == 0 ? a0 : (q == 1 ? a1 : (q == 2 ? a2 : a3));
-}
-
-// Philox-4x32-10 (Salmon et al. SC'11); identical to oracle/blokus_oracle.c:orc_philox.
-__device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
-        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-}
-// The sampler's draw for a state at `ply`: one Philox block serves four consecutive plies
-// (counter = (ply >> 2, game, stream, 0), word ply & 3), so a rollout recomputes it every fourth ply only.
-__device__ __forceinline__ uint32_t philox_word(const uint4 &b, uint32_t ply) {
-    const uint32_t i = ply & 3u;
-    return i == 0 ? b.x : (i == 1 ? b.y : (i == 2 ? b.z : b.w));
-}
-
-// k-th (0-based) set bit of w; requires popc(w) > k.  (__fns is emulated with ~500 instructions.)
-__device__ __forceinline__ int kth_set_bit(uint32_t w, int k) {
-    int pos = 0;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const int c = __popc((w >> pos) & ((1u << s) - 1u));
-        if (k >= c) { k -= c; pos += s; }
-    }
-    return pos;
-}
-
-// PTX shl clamps shift amounts above 31 to 32 (result 0); C's << would be undefined there.
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t sh) {
-    uint32_t r;
-    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));
-    return r;
-}
-
-__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kAllLanes, v, d);
-    return v;
-}
-
-// Board dimensions as seen by the device helpers.  The kernels are instantiated for <N=20, P=4> (every member a
-// compile-time constant after inlining) and for <0, 0> (runtime values from Geometry).
-struct Dims {
-    int N, P, A, score_rule;
-    uint32_t full;
-};
-template <int kN, int kP>
-__device__ __forceinline__ Dims make_dims(const Geometry &g) {
-    Dims d;
-    d.N = kN ? kN : g.N;
-    d.P = kP ? kP : g.P;
-    d.A = g.A;
-    d.score_rule = g.score_rule;
-    d.full = kN ? ((1u << kN) - 1u) : g.full;
-    return d;
-}
-
-// Dynamic work distribution: warps draw env indices from a global ticket counter instead of a fixed stride, so
-// nobody idles in the last wave (65,536 envs over 3,552 resident warps is 18.45 each) and uneven envs
-// (skipped players, finished games) even out.  The last block to finish resets the counters for the next launch.
-__device__ __forceinline__ int64_t next_ticket(unsigned long long *queue, int lane) {
-    unsigned long long t = 0;
-    if (lane == 0) t = atomicAdd(queue, 1ULL);
-    return static_cast<int64_t>(__shfl_sync(kAllLanes, t, 0));
-}
-__device__ __forceinline__ void queue_release(unsigned long long *queue) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned long long done = atomicAdd(queue + 1, 1ULL);
-        if (done == gridDim.x - 1) { queue[0] = 0ULL; queue[1] = 0ULL; }
-    }
-}
-
-// Per-warp view of one env held in registers (lane y = board row y).
-struct EnvRegs {
-    uint32_t own0, own1, own2, own3;   // this lane's row of each player's bitboard
-    uint32_t inv0, inv1, inv2, inv3;   // inventories (warp-uniform)
-    uint32_t sc01, sc23;               // int16 x 4 placed-squares scores (warp-uniform)
-    uint32_t meta, game;               // warp-uniform
-};
-
-// this lane's share of one env state as it sits in HBM: its row of each bitboard + one tail word
-struct EnvRaw {
-    uint32_t r0, r1, r2, r3, tail;
-};
-
-__device__ __forceinline__ EnvRaw env_fetch(const uint32_t *s, const Dims &g, int lane) {
-    const int N = g.N, P = g.P;
-    const bool in = lane < N;
-    EnvRaw w;
-    w.r0 = in ? __ldg(s + lane) : 0u;
-    w.r1 = in ? __ldg(s + N + lane) : 0u;
-    w.r2 = (in && P > 2) ? __ldg(s + 2 * N + lane) : 0u;
-    w.r3 = (in && P > 2) ? __ldg(s + 3 * N + lane) : 0u;
-    w.tail = lane < P + 4 ? __ldg(s + P * N + lane) : 0u;
-    return w;
-}
-
-__device__ __forceinline__ void env_unpack(EnvRegs &e, const EnvRaw &w, const Dims &g) {
-    const int P = g.P;
-    e.own0 = w.r0; e.own1 = w.r1; e.own2 = w.r2; e.own3 = w.r3;
-    e.inv0 = __shfl_sync(kAllLanes, w.tail, 0);
-    e.inv1 = __shfl_sync(kAllLanes, w.tail, 1);
-    e.inv2 = P > 2 ? __shfl_sync(kAllLanes, w.tail, 2) : 0u;
-    e.inv3 = P > 2 ? __shfl_sync(kAllLanes, w.tail, 3) : 0u;
-    e.meta = __shfl_sync(kAllLanes, w.tail, P);
-    e.game = __shfl_sync(kAllLanes, w.tail, P + 1);
-    e.sc01 = __shfl_sync(kAllLanes, w.tail, P + 2);
-    e.sc23 = __shfl_sync(kAllLanes, w.tail, P + 3);
-}
-
-__device__ __forceinline__ void env_load(EnvRegs &e, const uint32_t *s, const Dims &g, int lane) {
-    env_unpack(e, env_fetch(s, g, lane), g);
-}
-
-__device__ __forceinline__ void env_store(const EnvRegs &e, uint32_t *s, const Dims &g, int lane) {
-    const int N = g.N, P = g.P;
-    if (lane < N) {
-        s[lane] = e.own0;
-        s[N + lane] = e.own1;
-        if (P > 2) {
-            s[2 * N + lane] = e.own2;
-            s[3 * N + lane] = e.own3;
-        }
-    }
-    if (lane < P + 4) {
-        const int t = lane - P;
-        uint32_t v = sel4(e.inv0, e.inv1, e.inv2, e.inv3, lane);
-        if (t == 0) v = e.meta;
-        if (t == 1) v = e.game;
-        if (t == 2) v = e.sc01;
-        if (t == 3) v = e.sc23;
-        s[P * N + lane] = v;
-    }
-}
-
-__device__ __forceinline__ void env_fresh(EnvRegs &e, const Dims &g, uint32_t game) {
-    e.own0 = e.own1 = e.own2 = e.own3 = 0u;
-    e.inv0 = e.inv1 = kFullInv;
-    e.inv2 = e.inv3 = g.P > 2 ? kFullInv : 0u;
-    e.sc01 = e.sc23 = 0u;
-    e.meta = 0u;
-    e.game = game;
-}
-
-// rows of player q needed for legality: this lane's row of "free" and "diag/corner" boards
-__device__ __forceinline__ void prep_rows(const EnvRegs &e, int q, const Dims &g, int lane, uint32_t &fr0,
-                                          uint32_t &dg0) {
-    const uint32_t o = sel4(e.own0, e.own1, e.own2, e.own3, q);
-    const uint32_t occ = e.own0 | e.own1 | e.own2 | e.own3;
-    uint32_t up = __shfl_up_sync(kAllLanes, o, 1);
-    uint32_t dn = __shfl_down_sync(kAllLanes, o, 1);
-    if (lane == 0) up = 0u;
-    if (lane == 31) dn = 0u;
-    const uint32_t ud = up | dn;
-    const uint32_t adj = ud | (o << 1) | (o >> 1);
-    const bool first = sel4(e.inv0, e.inv1, e.inv2, e.inv3, q) == kFullInv;
-    const int n1 = g.N - 1;
-    const int cy = (g.P == 2) ? (q ? n1 : 0) : ((q & 2) ? n1 : 0);
-    const int cx = (g.P == 2) ? (q ? n1 : 0) : ((q & 1) ? n1 : 0);
-    const bool in = lane < g.N;
-    fr0 = in ? (~(occ | adj) & g.full) : 0u;
-    const uint32_t diag = ((ud << 1) | (ud >> 1)) & g.full;
-    dg0 = in ? (first ? (lane == cy ? (1u << cx) : 0u) : diag) : 0u;
-}
-
-// final-rule score of player q (R10); lastmono/inv decide the optional bonus
-__device__ __forceinline__ int final_score(const EnvRegs &e, int q, const Dims &g) {
-    const uint32_t packed = (q < 2) ? e.sc01 : e.sc23;
-    int s = static_cast<int>(static_cast<int16_t>((packed >> (16 * (q & 1))) & 0xffffu));
-    if (g.score_rule == 1 && sel4(e.inv0, e.inv1, e.inv2, e.inv3, q) == 0u)
-        s += 15 + (((e.meta >> (8 + q)) & 1u) ? 5 : 0);
-    return s;
-}
-
-// All 91 orientations against rows lane..lane+4 of the free / diagonal boards.  Stages one field per
-// (orientation, anchor row = lane) at fld[o*(N+1) - hsum(o) + lane] and returns this lane's OR of them.
-// Every (dy, dx) a 5-cell piece can reach satisfies dy + dx <= 4: 15 shifted copies of each board.
-template <bool kStage>
-__device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint32_t invc, uint32_t *fld, int N,
-                                                int lane) {
-    uint32_t fs[5][5], ds[5][5];
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {  // lanes >= N hold 0 and N <= 20, so out-of-range source lanes read 0
-        const uint32_t f = r ? __shfl_down_sync(kAllLanes, fr0, r) : fr0;
-        const uint32_t d = r ? __shfl_down_sync(kAllLanes, dg0, r) : dg0;
-#pragma unroll
-        for (int x = 0; x < 5; ++x) {
-            fs[r][x] = (r + x <= 4) ? (f >> x) : 0u;
-            ds[r][x] = (r + x <= 4) ? (d >> x) : 0u;
-        }
-    }
-    bool ok[6];
-#pragma unroll
-    for (int h = 1; h <= 5; ++h) ok[h] = lane <= N - h;
-    uint32_t anyacc = 0u;
-    const int np1 = N + 1;
-    uint32_t *fldp = fld + lane;
-#define BLK_PIECE_BEGIN(p) if ((invc >> (p)) & 1u) {
-#define BLK_ORIENT(o, p, h, w, n, hsum, y0, x0, y1, x1, y2, x2, y3, x3, y4, x4)                        \
-    {                                                                                                  \
-        const uint32_t f_ = (fs[y0][x0] & fs[y1][x1] & fs[y2][x2] & fs[y3][x3] & fs[y4][x4]) &         \
-                            (ds[y0][x0] | ds[y1][x1] | ds[y2][x2] | ds[y3][x3] | ds[y4][x4]);         \
-        anyacc |= f_;                                                                                  \
-        if (kStage && ok[h]) fldp[(o) * np1 - (hsum)] = f_;                                            \
-    }
-#define BLK_PIECE_ELSE(p) \
-    }                     \
-    else if (kStage) {
-#define BLK_ZERO(o, h, hsum) \
-    if (ok[h]) fldp[(o) * np1 - (hsum)] = 0u;
-#define BLK_PIECE_END(p) }
-#include "blk_orient.inc"
-#undef BLK_PIECE_BEGIN
-#undef BLK_ORIENT
-#undef BLK_PIECE_ELSE
-#undef BLK_ZERO
-#undef BLK_PIECE_END
-    return anyacc;
-}
-
-// mask word g (bits 32g..32g+31 of the action-id-ordered mask) gathered from the staged fields: generic form
-__device__ __forceinline__ uint32_t assemble_word(int g, const uint32_t *fld, const uint16_t *foff,
-                                                  const uint16_t *wsrc) {
-    uint32_t word = 0u;
-    int i = wsrc[g];
-    const int bit0 = g << 5;
-    while (true) {
-        const int off = static_cast<int>(foff[i]) - bit0;
-        if (off >= 32) break;
-        const uint32_t v = fld[i];
-        word |= off >= 0 ? (v << off) : (v >> (-off));
-        ++i;
-    }
-    return word;
-}
-
-// ... and the branch-free form used when at most three fields meet a word (N = 20: fields are 16-20 bits wide)
-__device__ __forceinline__ uint32_t assemble_word3(int g, const uint32_t *fld, const uint2 *wdesc) {
-    const uint2 d = wdesc[g];
-    const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(fld) + d.x);
-    return (p[0] >> (d.y & 31u)) | shl_clamp(p[1], __byte_perm(d.y, 0u, 0x4441u)) |
-           shl_clamp(p[2], __byte_perm(d.y, 0u, 0x4442u));
-}
-
-struct SmemTables {
-    const int32_t *obase;
-    const uint32_t *oinfo;
-    const uint32_t *ocells;
-    const uint16_t *foff;
-    const uint16_t *wsrc;
-    const uint16_t *fbase;
-    const uint8_t *f2o;
-    const uint2 *wdesc;
-    const uint2 *lut;
-};
-__device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, const TableLayout &t) {
-    SmemTables tb;
-    tb.obase = reinterpret_cast<const int32_t *>(tab + t.off_obase);
-    tb.oinfo = reinterpret_cast<const uint32_t *>(tab + t.off_oinfo);
-    tb.ocells = reinterpret_cast<const uint32_t *>(tab + t.off_ocells);
-    tb.foff = reinterpret_cast<const uint16_t *>(tab + t.off_foff);
-    tb.wsrc = reinterpret_cast<const uint16_t *>(tab + t.off_wsrc);
-    tb.fbase = reinterpret_cast<const uint16_t *>(tab + t.off_fbase);
-    tb.f2o = tab + t.off_f2o;
-    tb.wdesc = reinterpret_cast<const uint2 *>(tab + kOffWdesc);
-    tb.lut = reinterpret_cast<const uint2 *>(tab + kOffLut);
-    return tb;
-}
-
-// decode an action id into this lane's row bits of the footprint; returns false when out of range
-__device__ __forceinline__ bool decode_action(int act, const SmemTables &tb, const Dims &g, int lane,
-                                              uint32_t &pm, int &piece, int &ncells) {
-    pm = 0u; piece = 0; ncells = 0;
-    if (act < 0 || act >= g.A) return false;
-    int o = -1;
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        const int oo = lane + 32 * t;
-        const bool hit = oo < kOrients && tb.obase[oo] <= act && act < tb.obase[oo + 1];
-        const uint32_t b = __ballot_sync(kAllLanes, hit);
-        if (b) o = 32 * t + __ffs(b) - 1;
-    }
-    const uint32_t oi = tb.oinfo[o];
-    const uint32_t cells = tb.ocells[o];
-    piece = oi & 31;
-    const int w = (oi >> 12) & 15;
-    ncells = (oi >> 16) & 15;
-    const int W = g.N + 1 - w;
-    const int rem = act - tb.obase[o];
-    const int ay = rem / W;
-    const int ax = rem - ay * W;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        const int dy = (cells >> (6 * c)) & 7, dx = (cells >> (6 * c + 3)) & 7;
-        if (c < ncells && ay + dy == lane) pm |= 1u << (ax + dx);
-    }
-    return true;
-}
-
-// the same from a (field, bit) pair, as the rollout sampler finds it: no search, no division
-__device__ __forceinline__ void decode_field(int fsel, int bit, const SmemTables &tb, int lane, uint32_t &pm,
-                                             int &piece, int &ncells) {
-    const int o = tb.f2o[fsel];
-    const int ay = fsel - static_cast<int>(tb.fbase[o]);
-    const uint32_t oi = tb.oinfo[o], cells = tb.ocells[o];
-    piece = oi & 31;
-    ncells = (oi >> 16) & 15;
-    pm = 0u;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        const int dy = (cells >> (6 * c)) & 7, dx = (cells >> (6 * c + 3)) & 7;
-        if (c < ncells && ay + dy == lane) pm |= 1u << (bit + dx);
-    }
-}
-
-__device__ __forceinline__ void apply_placement(EnvRegs &e, int p, uint32_t pm, int piece, int ncells) {
-    const uint32_t clr = ~(1u << piece);
-    if (p == 0) { e.own0 |= pm; e.inv0 &= clr; }
-    if (p == 1) { e.own1 |= pm; e.inv1 &= clr; }
-    if (p == 2) { e.own2 |= pm; e.inv2 &= clr; }
-    if (p == 3) { e.own3 |= pm; e.inv3 &= clr; }
-    uint32_t &sc = (p < 2) ? e.sc01 : e.sc23;
-    const int sh = 16 * (p & 1);
-    const uint32_t cur = (sc >> sh) & 0xffffu;
-    sc = (sc & ~(0xffffu << sh)) | (((cur + ncells) & 0xffffu) << sh);
-    uint32_t m = e.meta;
-    m = (m & ~(1u << (8 + p))) | ((piece == 0 ? 1u : 0u) << (8 + p));   // lastmono
-    m += 1u << 16;                                                         // ply
-    e.meta = m;
-}
-
-// winners bitmask + value of lane q (<P): 3 sole winner, 1 tied winner, -1 otherwise (blokus_wrapper.py:177-185)
-__device__ __forceinline__ float terminal_value(const EnvRegs &e, const Dims &g, int lane, int &my_score) {
-    my_score = lane < g.P ? final_score(e, lane, g) : -32768;
-    int best = my_score;
-#pragma unroll
-    for (int d = 1; d < 4; d <<= 1) best = max(best, __shfl_xor_sync(kAllLanes, best, d));
-    const uint32_t win = __ballot_sync(kAllLanes, lane < g.P && my_score == best);
-    const bool mine = (win >> lane) & 1u;
-    return mine ? (__popc(win) == 1 ? 3.f : 1.f) : -1.f;
-}
-
-// ---------------------------------------------------------------------------------------------
-// step / legal-mask kernel
-// ---------------------------------------------------------------------------------------------
-// kFmt: 0 = no mask output, 1 = bit-packed, 2 = bytes through 16 B vector stores, 3 = bytes into an unaligned buffer.
-template <int kN, int kP, int kFmt, bool kSample>
-__global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const KParams kp) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const Geometry &gg = kp.g;
-    const Dims g = make_dims<kN, kP>(gg);
-    const blk_step_args &a = kp.a;
-    unsigned char *tab = smem;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kp.t.bytes);
-    unsigned char *scratch = smem + kp.t.bytes + 16;
-    tma_load_tables(tab, kp.tables, kp.t.bytes, bar);
-    const SmemTables tb = make_tables(tab, kp.t);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int N = g.N, P = g.P;
-    const int sw = P * N + P + 4;
-    const int fld_words = kN == 20 ? 1668 : gg.fld_words;
-    const int mw = kN == 20 ? 952 : gg.mw;
-    const int rounds = kN == 20 ? 30 : gg.rounds;
-    const int mask_bytes = kN == 20 ? (30433 + BLK_ROW_ALIGN - 1) / BLK_ROW_ALIGN * BLK_ROW_ALIGN : gg.mask_bytes;
-    const bool fast3 = kN == 20 ? true : (gg.fast3 != 0);
-    uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * gg.warp_smem);
-    uint32_t *tots = fld + fld_words;                                  // 32 per-pass popcount totals (sampler)
-    const int64_t n = a.n;
-    const int64_t mstride = a.mask_stride;
-    const bool want_count = a.legal_count != nullptr;
-    const uint32_t rot_lo = (lane & 1) ? 19u : 3u, rot_hi = (lane & 1) ? 11u : 27u;   // 16-bit half -> LUT byte offsets
-    const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);
-    const unsigned char *lutb = reinterpret_cast<const unsigned char *>(tb.lut);
-    const uint2 *wdl = tb.wdesc + lane;
-    for (int i = (kN == 20 ? 1665 : gg.nf) + lane; i < fld_words; i += 32) fld[i] = 0u;   // gather padding stays zero
-
-    // software pipeline over this warp's envs: the next env's 352 B and action are fetched while the current one
-    // is processed (a warp handles its envs serially; without this every env starts with an exposed HBM round trip)
-    int64_t env = next_ticket(kp.queue, lane);
-    int64_t env_next = next_ticket(kp.queue, lane), env_after = 0;
-    EnvRaw raw_next = {};
-    int act_next = BLK_ACTION_NONE;
-    if (env < n) {
-        raw_next = env_fetch(a.state_in + env * sw, g, lane);
-        if (a.action != nullptr) act_next = __ldg(a.action + env);
-    }
-    for (; env < n; env = env_next, env_next = env_after) {
-        EnvRegs e;
-        env_unpack(e, raw_next, g);
-        const int act = act_next;
-        if (env_next < n) {
-            raw_next = env_fetch(a.state_in + env_next * sw, g, lane);
-            if (a.action != nullptr) act_next = __ldg(a.action + env_next);
-        }
-        env_after = next_ticket(kp.queue, lane);
-        const bool was_done = (e.meta >> 4) & 1u;
-        const int mover = e.meta & 15u;
-        uint32_t flags = 0u;
-        bool moved = false;
-
-        if (act != BLK_ACTION_NONE) {
-            uint32_t pm; int piece, ncells;
-            bool legal = !was_done && decode_action(act, tb, g, lane, pm, piece, ncells);
-            if (legal) {
-                uint32_t fr0, dg0;
-                prep_rows(e, mover, g, lane, fr0, dg0);
-                const bool avail = (sel4(e.inv0, e.inv1, e.inv2, e.inv3, mover) >> piece) & 1u;
-                const bool bad = __any_sync(kAllLanes, (pm & ~fr0) != 0u);
-                const bool touch = __any_sync(kAllLanes, (pm & dg0) != 0u);
-                legal = avail && !bad && touch;
-            }
-            if (legal) { apply_placement(e, mover, pm, piece, ncells); moved = true; }
-            else flags |= BLK_FLAG_ILLEGAL;
-        }
-
-        // ---- next mover (R8 auto-skip), terminal detection (R9), optional auto-reset ----
-        bool have = false, ended = false;
-        float tval = 0.f;
-        int fscore = 0;
-        if (lane < P) fscore = final_score(e, lane, g);
-        if (was_done) {
-            ended = true;
-            tval = terminal_value(e, g, lane, fscore);
-        } else {
-            int cand = moved ? mover : (mover == 0 ? P - 1 : mover - 1);
-            int tries = moved ? P : 1;
-            bool did_reset = false;
-#pragma unroll 1
-            while (true) {
-                cand = (cand + 1 == P) ? 0 : cand + 1;
-                uint32_t fr0, dg0;
-                prep_rows(e, cand, g, lane, fr0, dg0);
-                const uint32_t acc = eval_fields<true>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
-                if (__any_sync(kAllLanes, acc != 0u)) { have = true; break; }
-                if (--tries > 0) continue;
-                if (!moved) break;                      // mask-only call on a state whose mover is stuck
-                ended = true;                           // nobody can move: the game is over
-                tval = terminal_value(e, g, lane, fscore);
-                if ((a.options & BLK_OPT_AUTO_RESET) && !did_reset) {
-                    env_fresh(e, g, e.game + 1u);
-                    did_reset = true; cand = P - 1; tries = 1;
-                    continue;
-                }
-                e.meta |= 1u << 4;                      // done; mover stays = last mover
-                break;
-            }
-            if (have) e.meta = (e.meta & ~15u) | static_cast<uint32_t>(cand);
-        }
-        if (ended) flags |= BLK_FLAG_DONE;
-        if (!have) {                                   // terminal (or stuck) state: empty mask
-            for (int i = lane; i < fld_words; i += 32) fld[i] = 0u;
-        }
-        __syncwarp();
-
-        // ---- gather the action-id-ordered mask from the staged fields and stream it out ----
-        int cnt = 0;
-        if (kFmt != 0 || kSample || want_count) {
-            unsigned char *row = reinterpret_cast<unsigned char *>(a.mask) + env * mstride + 16 * lane;
-            uint32_t *wrow = reinterpret_cast<uint32_t *>(a.mask) + env * mstride + lane;
-#pragma unroll(kEmitUnroll)
-            for (int r = 0; r < (kN == 20 ? 30 : rounds); ++r) {
-                uint32_t word;
-                if (fast3) word = assemble_word3(r << 5, fld, wdl);
-                else word = ((r << 5) + lane) < mw ? assemble_word((r << 5) + lane, fld, tb.foff, tb.wsrc) : 0u;
-                const int pc = __popc(word);
-                if (kSample) {
-                    const int tot = __reduce_add_sync(kAllLanes, pc);
-                    if (lane == 0) tots[r] = tot;
-                    cnt += tot;
-                } else {
-                    cnt += pc;
-                }
-                if (kFmt == 1) {
-                    if (r < (kN == 20 ? 29 : rounds - 1) || (r << 5) + lane < mw) wrow[r << 5] = word;
-                } else if (kFmt == 2) {
-                    // 32 words -> 1024 bytes; each lane expands 16 bits through the byte LUT (two 8-byte entries) and
-                    // writes 16 B, so one warp store covers 512 contiguous bytes
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t w2 = __shfl_sync(kAllLanes, word, h ? src_hi : src_lo);
-                        const uint2 lo = *reinterpret_cast<const uint2 *>(lutb + (__funnelshift_l(w2, w2, rot_lo) & 0x7f8u));
-                        const uint2 hi = *reinterpret_cast<const uint2 *>(lutb + (__funnelshift_l(w2, w2, rot_hi) & 0x7f8u));
-                        const int boff = (r << 10) + 512 * h;
-                        if (r < (kN == 20 ? 29 : rounds - 1) || boff + 16 * lane < mask_bytes)
-                            BLK_STORE16(reinterpret_cast<uint4 *>(row + boff), make_uint4(lo.x, lo.y, hi.x, hi.y));
-                    }
-                } else if (kFmt == 3) {  // unaligned caller buffer: correct but slow byte stores
-                    unsigned char *urow = reinterpret_cast<unsigned char *>(a.mask) + env * mstride;
-                    for (int b = 0; b < 32; ++b) {
-                        const int idx = (((r << 5) + lane) << 5) + b;
-                        if (idx < g.A) urow[idx] = static_cast<unsigned char>((word >> b) & 1u);
-                    }
-                }
-            }
-            if (!kSample) cnt = warp_sum(cnt);
-        }
-        if (want_count && lane == 0) a.legal_count[env] = cnt;
-
-        // ---- uniform random legal action for the new mover: k = mulhi(u32, n), k-th set bit ascending ----
-        if (kSample) {
-            int pick = -1;
-            if (cnt > 0) {
-                __syncwarp();
-                const uint32_t ply = e.meta >> 16;
-                const uint32_t u = philox_word(philox4(ply >> 2, e.game, 0u, 0u, static_cast<uint32_t>(a.seed),
-                                                       static_cast<uint32_t>(a.seed >> 32) ^ (a.env_id_base + static_cast<uint32_t>(env))), ply);
-                int k = static_cast<int>(__umulhi(u, static_cast<uint32_t>(cnt)));
-                // level 1: which pass of 32 words
-                const int tot = lane < rounds ? static_cast<int>(tots[lane]) : 0;
-                const int incl = warp_incl_scan(tot, lane);
-                const int R = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
-                k -= __shfl_sync(kAllLanes, incl - tot, R);
-                // level 2: which word of that pass (re-gathered: cheaper than keeping 952 popcounts around)
-                const int gi = (R << 5) + lane;
-                uint32_t word;
-                if (fast3) word = assemble_word3(gi, fld, tb.wdesc);
-                else word = gi < mw ? assemble_word(gi, fld, tb.foff, tb.wsrc) : 0u;
-                const int c2 = __popc(word);
-                const int incl2 = warp_incl_scan(c2, lane);
-                const int J = __ffs(__ballot_sync(kAllLanes, k < incl2)) - 1;
-                k -= __shfl_sync(kAllLanes, incl2 - c2, J);
-                const uint32_t wsel = __shfl_sync(kAllLanes, word, J);
-                pick = (((R << 5) + J) << 5) + kth_set_bit(wsel, k);
-            }
-            if (lane == 0) a.next_action[env] = pick;
-        }
-
-        // ---- per-step outputs and state write-back ----
-        if (lane < P) {
-            if (a.terminal != nullptr) a.terminal[env * P + lane] = ended ? tval : 0.f;
-            if (a.scores != nullptr) a.scores[env * P + lane] = static_cast<int16_t>(fscore);
-        }
-        if (a.flags != nullptr && lane == 0) a.flags[env] = static_cast<uint8_t>(flags);
-        if (a.state_out != nullptr) env_store(e, a.state_out + env * sw, g, lane);
-        __syncwarp();
-    }
-    queue_release(kp.queue);
-}
 
 // ---------------------------------------------------------------------------------------------
 // small streaming kernels
@@ -805,133 +137,6 @@ __global__ void ended_kernel(const uint32_t *__restrict__ state, uint8_t *flags,
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// rollout kernel: one warp plays one game to the end, state in registers, fields in shared memory
-// ---------------------------------------------------------------------------------------------
-struct RParams {
-    blk_rollout_args a;
-    const unsigned char *tables;
-    TableLayout t;
-    Geometry g;
-    unsigned long long *queue;
-};
-
-template <int kN, int kP>
-__global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(const RParams rp) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const Geometry &gg = rp.g;
-    const Dims g = make_dims<kN, kP>(gg);
-    const blk_rollout_args &a = rp.a;
-    unsigned char *tab = smem;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + rp.t.bytes);
-    unsigned char *scratch = smem + rp.t.bytes + 16;
-    tma_load_tables(tab, rp.tables, rp.t.bytes, bar);
-    const SmemTables tb = make_tables(tab, rp.t);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * gg.warp_smem);
-    const int N = g.N, P = g.P;
-    const int sw = P * N + P + 4;
-    const int nf = kN == 20 ? 1665 : gg.nf;
-    const int64_t total = a.n_roots * a.per_root;
-    const int per = (nf + 31) >> 5;   // contiguous fields per lane for the k-th-bit search (53 at N = 20)
-
-    for (int64_t gid = next_ticket(rp.queue, lane); gid < total; gid = next_ticket(rp.queue, lane)) {
-        const int64_t root = gid / a.per_root;
-        EnvRegs e;
-        env_load(e, a.roots + root * sw, g, lane);
-        const uint32_t key0 = static_cast<uint32_t>(a.seed);
-        const uint32_t key1 = static_cast<uint32_t>(a.seed >> 32) ^ (a.rollout_id_base + static_cast<uint32_t>(gid));
-        int nply = 0;
-        uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
-        int rnd_block = -1;
-        bool over = (e.meta >> 4) & 1u;
-        // the root's mover is evaluated first; afterwards every player gets a try after each placement (R8)
-        int cand = static_cast<int>(e.meta & 15u);
-        cand = cand == 0 ? P - 1 : cand - 1;
-        int tries = 1;
-#pragma unroll 1
-        while (!over) {
-            cand = (cand + 1 == P) ? 0 : cand + 1;
-            uint32_t fr0, dg0;
-            prep_rows(e, cand, g, lane, fr0, dg0);
-            const uint32_t acc = eval_fields<true>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
-            if (!__any_sync(kAllLanes, acc != 0u)) {
-                if (--tries > 0) continue;
-                e.meta |= 1u << 4;
-                over = true;
-                break;
-            }
-            __syncwarp();
-            e.meta = (e.meta & ~15u) | static_cast<uint32_t>(cand);
-            // count legal actions: lane sums popcounts over its contiguous chunk of fields (field order = id order)
-            int mine = 0;
-            if (kN == 20) {                     // 1665 fields = 32 x 52 (+1 for lane 31): 13 conflict-free LDS.128 per lane
-                const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 13 * lane;
-#pragma unroll
-                for (int j = 0; j < 13; ++j) {
-                    const uint4 x = f4[j];
-                    mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
-                }
-                if (lane == 31) mine += __popc(fld[1664]);
-            } else {
-                for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
-            }
-            const int incl = warp_incl_scan(mine, lane);
-            const int cnt = __shfl_sync(kAllLanes, incl, 31);
-            const uint32_t ply = e.meta >> 16;
-            if (static_cast<int>(ply >> 2) != rnd_block) {
-                rnd = philox4(ply >> 2, e.game, 1u, 0u, key0, key1);
-                rnd_block = static_cast<int>(ply >> 2);
-            }
-            int k = static_cast<int>(__umulhi(philox_word(rnd, ply), static_cast<uint32_t>(cnt)));
-            const int L = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
-            k -= __shfl_sync(kAllLanes, incl - mine, L);
-            // second level: the chunk of lane L, 32 fields at a time
-            const int chunk = kN == 20 ? 52 : per;
-            const int chunk_len = kN == 20 ? (L == 31 ? 53 : 52) : per;
-            int fsel = -1, kk = 0;
-            for (int half = 0; half * 32 < chunk_len; ++half) {
-                const int j = half * 32 + lane;
-                const int i = L * chunk + j;
-                const int c = (j < chunk_len && i < nf) ? __popc(fld[i]) : 0;
-                const int inc2 = warp_incl_scan(c, lane);
-                const uint32_t b = __ballot_sync(kAllLanes, k < inc2);
-                if (b) {
-                    const int J = __ffs(b) - 1;
-                    kk = k - __shfl_sync(kAllLanes, inc2 - c, J);
-                    fsel = L * chunk + half * 32 + J;
-                    break;
-                }
-                k -= __shfl_sync(kAllLanes, inc2, 31);
-            }
-            const int bit = kth_set_bit(fld[fsel], kk);
-            if (a.action_log != nullptr && lane == 0 && nply < a.log_stride - 1)
-                a.action_log[gid * a.log_stride + nply] = static_cast<uint16_t>(tb.foff[fsel] + bit);
-            uint32_t pm; int piece, ncells;
-            decode_field(fsel, bit, tb, lane, pm, piece, ncells);
-            apply_placement(e, cand, pm, piece, ncells);
-            ++nply;
-            tries = P;
-            __syncwarp();
-        }
-        int fscore;
-        const float tval = terminal_value(e, g, lane, fscore);
-        const uint32_t win = __ballot_sync(kAllLanes, lane < P && tval > 0.f);
-        if (lane < P) {
-            a.final_scores[gid * P + lane] = static_cast<int16_t>(fscore);
-            if (a.value_sum != nullptr) atomicAdd(a.value_sum + root * P + lane, tval);
-        }
-        if (lane == 0) {
-            if (a.winners != nullptr) a.winners[gid] = static_cast<uint8_t>(win);
-            if (a.plies != nullptr) a.plies[gid] = nply;
-            if (a.action_log != nullptr) a.action_log[gid * a.log_stride + min(nply, a.log_stride - 1)] = 0xFFFFu;
-        }
-        __syncwarp();
-    }
-    queue_release(rp.queue);
-}
-
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -948,8 +153,7 @@ struct blk_engine {
     int step_smem = 0;
     int step_blocks_per_sm = 0, rollout_blocks_per_sm = 0;
     bool special = false;
-    void (*step_fn[4][2])(const KParams) = {};      // [mask format variant][sampler]
-    void (*rollout_fn)(const RParams) = nullptr;
+    KernelSet ks = {};                               // step[mask format variant][sampler], rollout
     std::vector<int32_t> obase;        // host copies for blk_action_to_cells
     std::vector<int16_t> act_o, act_y, act_x;
 };
@@ -1102,31 +306,29 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     int rc = build_tables(h);
     if (rc != BLK_OK) { blk_destroy(h); return rc; }
     h->step_smem = h->t.bytes + 16 + kWarps * h->g.warp_smem;
-    // specialised <20,4> kernels for the headline geometry, runtime-dimension <0,0> kernels for everything else
-    h->special = cfg->board_size == 20 && cfg->num_players == 4;
-#define BLK_STEP_VARIANTS(NN, PP)                                                                     \
-    do {                                                                                              \
-        h->step_fn[0][0] = step_kernel<NN, PP, 0, false>; h->step_fn[0][1] = step_kernel<NN, PP, 0, true>; \
-        h->step_fn[1][0] = step_kernel<NN, PP, 1, false>; h->step_fn[1][1] = step_kernel<NN, PP, 1, true>; \
-        h->step_fn[2][0] = step_kernel<NN, PP, 2, false>; h->step_fn[2][1] = step_kernel<NN, PP, 2, true>; \
-        h->step_fn[3][0] = step_kernel<NN, PP, 3, false>; h->step_fn[3][1] = step_kernel<NN, PP, 3, true>; \
-    } while (0)
-    if (h->special) BLK_STEP_VARIANTS(20, 4); else BLK_STEP_VARIANTS(0, 0);
-#undef BLK_STEP_VARIANTS
-    h->rollout_fn = h->special ? rollout_kernel<20, 4> : rollout_kernel<0, 0>;
+    // specialised kernels for the geometries the reference's configs name, runtime-dimension kernels otherwise
+    const int N = cfg->board_size, P = cfg->num_players;
+    int geom = 0;
+    if (N == 20 && P == 4) { h->ks = kernels_20_4(); geom = 1; }
+    else if (N == 20 && P == 2) { h->ks = kernels_20_2(); geom = 2; }
+    else if (N == 14 && P == 4) { h->ks = kernels_14_4(); geom = 3; }
+    else if (N == 14 && P == 2) { h->ks = kernels_14_2(); geom = 4; }
+    else if (N == 7 && P == 2) { h->ks = kernels_7_2(); geom = 5; }
+    else h->ks = kernels_0_0();
+    h->special = geom != 0;
     // the attribute is per function, not per engine: only ever raise it (engines of several board sizes coexist)
-    static int s_max_smem[16][2] = {};
-    int &cur_max = s_max_smem[cfg->device & 15][h->special ? 1 : 0];
+    static int s_max_smem[16][6] = {};
+    int &cur_max = s_max_smem[cfg->device & 15][geom];
     if (h->step_smem > cur_max) {
-        cudaError_t err = cudaFuncSetAttribute(h->rollout_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+        cudaError_t err = cudaFuncSetAttribute(h->ks.rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
         for (int f = 0; f < 4 && err == cudaSuccess; ++f)
             for (int sm = 0; sm < 2 && err == cudaSuccess; ++sm)
-                err = cudaFuncSetAttribute(h->step_fn[f][sm], cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+                err = cudaFuncSetAttribute(h->ks.step[f][sm], cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
         if (err != cudaSuccess) { blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed"); }
         cur_max = h->step_smem;
     }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_blocks_per_sm, h->step_fn[2][1], kWarps * 32, h->step_smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, h->rollout_fn, kWarps * 32, h->step_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_blocks_per_sm, h->ks.step[2][1], kWarps * 32, h->step_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, h->ks.rollout, kWarps * 32, h->step_smem);
     if (h->step_blocks_per_sm < 1 || h->rollout_blocks_per_sm < 1) { blk_destroy(h); return fail(BLK_ERR_CUDA, "kernel does not fit on an SM"); }
     *out = h;
     return BLK_OK;
@@ -1194,7 +396,7 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
     if (variant == BLK_MASK_BYTES &&
         ((args->mask_stride & 15) != 0 || (reinterpret_cast<uintptr_t>(args->mask) & 15) != 0 || args->mask_stride < h->g.mask_bytes))
         variant = 3;
-    h->step_fn[variant][args->next_action != nullptr ? 1 : 0]<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(kp);
+    h->ks.step[variant][args->next_action != nullptr ? 1 : 0]<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(kp);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
 }
@@ -1246,7 +448,7 @@ int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream) {
     rp.a = *args; rp.tables = h->d_tables; rp.t = h->t; rp.g = h->g;
     rp.queue = h->d_queue + 2 * (h->launch_seq++ % kQueueSlots);
     const int grid = grid_for(args->n_roots * args->per_root, kWarps, h->sm_count, h->rollout_blocks_per_sm);
-    h->rollout_fn<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(rp);
+    h->ks.rollout<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(rp);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
 }

@@ -1,0 +1,13 @@
+// blk_inst.cu -- instantiates the step / rollout kernels of ONE (N, P) specialisation.
+// Compiled once per geometry: nvcc -DBLK_INST_N=20 -DBLK_INST_P=4 ... (see blokus_rl_b200/build.py).
+#include "blk_kernels.cuh"
+
+#ifndef BLK_INST_N
+#error "compile with -DBLK_INST_N=<board size or 0> -DBLK_INST_P=<players or 0>"
+#endif
+#define BLK_CAT_(a, b, c) kernels_##a##_##b
+#define BLK_CAT(a, b) BLK_CAT_(a, b, )
+
+namespace blk {
+KernelSet BLK_CAT(BLK_INST_N, BLK_INST_P)() { return make_kernel_set<BLK_INST_N, BLK_INST_P>(); }
+}  // namespace blk

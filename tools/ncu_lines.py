@@ -23,8 +23,8 @@ from pathlib import Path
 def sass_lines(so: Path, kernel: str):
     tmp = Path(tempfile.mkdtemp())
     subprocess.check_call(["cuobjdump", "-xelf", "all", str(so.resolve())], cwd=tmp, stdout=subprocess.DEVNULL)
-    cubin = next(tmp.glob("*.cubin"))
-    txt = subprocess.run(["nvdisasm", "--print-line-info", str(cubin)], capture_output=True, text=True).stdout
+    txt = "\n".join(subprocess.run(["nvdisasm", "--print-line-info", str(c)], capture_output=True, text=True).stdout
+                    for c in sorted(tmp.glob("*.cubin")))     # one cubin per kernel specialisation object
     out, cur_line, active = [], ("?", 0), False
     for ln in txt.splitlines():
         if ln.startswith(".text."):
