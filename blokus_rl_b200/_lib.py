@@ -21,6 +21,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "blk_last_error", "blk_abi_version", "blk_create", "blk_destroy", "blk_get_info", "blk_action_to_cells",
     "blk_reset", "blk_step", "blk_observe", "blk_board_contents", "blk_game_ended", "blk_rollout",
+    "blk_puct_last_error", "blk_puct_select", "blk_puct_expand", "blk_puct_backup", "blk_puct_advance",
 )
 
 
@@ -52,6 +53,22 @@ class BlkRolloutArgs(C.Structure):
     ]
 
 
+class BlkPuctForest(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("num_trees", "num_players", "num_actions", "mask_stride", "node_capacity",
+                                          "edge_capacity", "max_depth")] +
+                [(n, C.c_void_p) for n in ("node_edge0", "node_nedge", "node_state", "node_mover", "node_terminal",
+                                           "node_term_value", "edge_action", "edge_child", "edge_n", "edge_q", "edge_p",
+                                           "root", "path", "path_len", "status", "leaf_node", "leaf_edge", "src_slot",
+                                           "step_action", "scores", "counters")])
+
+
+class BlkPuctExpandArgs(C.Structure):
+    _fields_ = [("new_slot_base", C.c_int32), ("state_words", C.c_int32), ("meta_word", C.c_int32),
+                ("attach_only", C.c_int32), ("new_states", C.c_void_p), ("mask", C.c_void_p), ("flags", C.c_void_p),
+                ("terminal", C.c_void_p), ("prior", C.c_void_p), ("prior_dtype", C.c_int32), ("prior_stride", C.c_int64),
+                ("value", C.c_void_p)]
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -81,6 +98,11 @@ def load() -> C.CDLL:
     lib.blk_board_contents.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.blk_game_ended.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.blk_rollout.argtypes = [C.c_void_p, C.POINTER(BlkRolloutArgs), C.c_void_p]
+    lib.blk_puct_last_error.restype = C.c_char_p
+    lib.blk_puct_select.argtypes = [C.POINTER(BlkPuctForest), C.c_double, C.c_int32, C.c_void_p]
+    lib.blk_puct_expand.argtypes = [C.POINTER(BlkPuctForest), C.POINTER(BlkPuctExpandArgs), C.c_void_p]
+    lib.blk_puct_backup.argtypes = [C.POINTER(BlkPuctForest), C.c_void_p]
+    lib.blk_puct_advance.argtypes = [C.POINTER(BlkPuctForest), C.c_void_p, C.c_void_p]
     if lib.blk_abi_version() != ABI_VERSION:
         raise EngineError("libblokus_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -16,7 +16,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "build"
 OUT = PKG / "libblokus_b200.so"
-DEPS = [CSRC / "blk_engine.cu", CSRC / "blk_inst.cu", CSRC / "blk_kernels.cuh", CSRC / "blk_orient.inc",
+DEPS = [CSRC / "blk_engine.cu", CSRC / "blk_inst.cu", CSRC / "blk_puct.cu", CSRC / "blk_kernels.cuh", CSRC / "blk_orient.inc",
         ROOT / "include" / "blokus_b200.h"]
 GEOMETRIES = [(20, 4), (20, 2), (14, 4), (14, 2), (7, 2), (0, 0)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -27,7 +27,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | N
         return OUT
     OBJ.mkdir(exist_ok=True)
     flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (extra_flags or [])
-    jobs = [(OBJ / "blk_engine.o", ["nvcc", *flags, "-c", str(CSRC / "blk_engine.cu")])]
+    jobs = [(OBJ / "blk_engine.o", ["nvcc", *flags, "-c", str(CSRC / "blk_engine.cu")]),
+            (OBJ / "blk_puct.o", ["nvcc", *flags, "-c", str(CSRC / "blk_puct.cu")])]
     for n, p in GEOMETRIES:
         jobs.append((OBJ / f"blk_inst_{n}_{p}.o",
                      ["nvcc", *flags, f"-DBLK_INST_N={n}", f"-DBLK_INST_P={p}", "-c", str(CSRC / "blk_inst.cu")]))

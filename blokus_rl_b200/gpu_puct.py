@@ -1,0 +1,155 @@
+"""Device-resident batched PUCT search: B trees live in GPU arrays and every
+simulation of all B trees is five kernel launches with no host synchronisation:
+
+    blk_puct_select  ->  blk_step (opened edges, legal masks)  ->  evaluator  ->  blk_puct_expand  ->  blk_puct_backup
+
+Per tree the arithmetic is that of ``blokus_rl/alphazero/mcts.py`` in float64 (see csrc/blk_puct.cu for the
+quirks it reproduces); ``tests/test_gpu_puct.py`` checks visit counts / Q / per-simulation score vectors against
+golden vectors produced by the unmodified reference file.  Unlike the host-side :class:`BatchedMCTS`, nodes are
+keyed by path, not by ``hash(board cells)``; the two coincide unless two move orders reach the same board inside
+one search.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .mcts import UniformEvaluator
+
+
+class GpuPuct:
+    def __init__(self, engine, evaluator=None, num_trees: int = 256, max_simulations: int = 4096,
+                 mean_edges_per_node: int = 256, max_depth: int = 96):
+        self.eng = engine
+        self.evaluator = evaluator or UniformEvaluator()
+        self.B, self.P, self.A = num_trees, engine.num_players, engine.num_actions
+        self._lib = _lib.load()
+        dev = engine.device
+        self.node_cap = num_trees * (max_simulations + 2)
+        self.edge_cap = self.node_cap * mean_edges_per_node
+        self.max_depth = max_depth
+        i32 = dict(dtype=torch.int32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        t = self.t = {
+            "node_edge0": torch.empty(self.node_cap, **i32), "node_nedge": torch.empty(self.node_cap, **i32),
+            "node_state": torch.empty(self.node_cap, **i32),
+            "node_mover": torch.empty(self.node_cap, dtype=torch.int8, device=dev),
+            "node_terminal": torch.empty(self.node_cap, dtype=torch.int8, device=dev),
+            "node_term_value": torch.empty((self.node_cap, self.P), **f64),
+            "edge_action": torch.empty(self.edge_cap, **i32), "edge_child": torch.empty(self.edge_cap, **i32),
+            "edge_n": torch.empty(self.edge_cap, **f64), "edge_q": torch.empty(self.edge_cap, **f64),
+            "edge_p": torch.empty(self.edge_cap, **f64),
+            "root": torch.empty(self.B, **i32), "path": torch.empty((self.B, max_depth), **i32),
+            "path_len": torch.zeros(self.B, **i32), "status": torch.zeros(self.B, **i32),
+            "leaf_node": torch.zeros(self.B, **i32), "leaf_edge": torch.zeros(self.B, **i32),
+            "src_slot": torch.zeros(self.B, **i32), "step_action": torch.zeros(self.B, **i32),
+            "scores": torch.zeros((self.B, self.P), **f64), "counters": torch.zeros(4, **i32),
+        }
+        self.pool = torch.empty((self.node_cap, engine.state_words), dtype=torch.int32, device=dev)
+        self.used = 0
+        self.forest = _lib.BlkPuctForest(self.B, self.P, self.A, engine.mask_bytes, self.node_cap, self.edge_cap, max_depth,
+                                         *[t[n].data_ptr() for n in (
+                                             "node_edge0", "node_nedge", "node_state", "node_mover", "node_terminal",
+                                             "node_term_value", "edge_action", "edge_child", "edge_n", "edge_q", "edge_p",
+                                             "root", "path", "path_len", "status", "leaf_node", "leaf_edge", "src_slot",
+                                             "step_action", "scores", "counters")])
+        self.buf = engine.make_buffers(self.B, "bytes")
+        self.launches = 0
+        self._meta = self.P * engine.board_size + self.P
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.eng.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.EngineError(f"blk_puct error {rc}: {self._lib.blk_puct_last_error().decode()}")
+
+    # ---- roots ------------------------------------------------------------------------------------------
+    def set_roots(self, states: torch.Tensor) -> None:
+        """Start B fresh trees at ``states`` (int32 [B, state_words])."""
+        assert states.shape == (self.B, self.eng.state_words)
+        t, B = self.t, self.B
+        self.pool[:B] = states
+        self.used = B
+        flags, term, _ = self.eng.game_ended(states)
+        ar = torch.arange(B, dtype=torch.int32, device=states.device)
+        t["root"].copy_(ar)
+        t["node_state"][:B] = ar
+        t["node_edge0"][:B] = -1
+        t["node_nedge"][:B] = 0
+        t["node_mover"][:B] = (states[:, self._meta] & 15).to(torch.int8)
+        t["node_terminal"][:B] = (flags & 1).to(torch.int8)
+        t["node_term_value"][:B] = term.to(torch.float64)
+        t["counters"].copy_(torch.tensor([B, 0, 0, 0], dtype=torch.int32))
+
+    # ---- one simulation of every tree ---------------------------------------------------------------------------
+    def _step_and_expand(self, attach_only: bool):
+        t, B, eng = self.t, self.B, self.eng
+        if self.used + B > self.node_cap:
+            raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
+        src = self.pool.index_select(0, t["src_slot"].long())
+        dst = self.pool[self.used: self.used + B]
+        out = eng.step(src, t["step_action"], out_states=dst, buffers=self.buf, mask="bytes", want_count=False,
+                       want_scores=False)
+        prior, pd, ps, value = None, 0, 0, None
+        if not attach_only and not isinstance(self.evaluator, UniformEvaluator):
+            p, v = self.evaluator.evaluate(eng, dst, out.mask)
+            prior = p.contiguous()
+            pd = 2 if prior.dtype == torch.float64 else 1
+            if pd == 1:
+                prior = prior.float()
+            ps = prior.stride(0)
+            value = v.to(torch.float64).contiguous()
+        args = _lib.BlkPuctExpandArgs(self.used, eng.state_words, self._meta, int(attach_only), dst.data_ptr(),
+                                      out.mask_raw.data_ptr(), out.flags.data_ptr(), out.terminal.data_ptr(),
+                                      None if prior is None else prior.data_ptr(), pd, ps,
+                                      None if value is None else value.data_ptr())
+        self._check(self._lib.blk_puct_expand(C.byref(self.forest), C.byref(args), self._stream()))
+        self.used += B
+        self.launches += 3 if prior is None else 4
+
+    def simulate(self, cpuct: float = 1.0, epsilon_fix: bool = True) -> None:
+        self._check(self._lib.blk_puct_select(C.byref(self.forest), float(cpuct), int(epsilon_fix), self._stream()))
+        self._step_and_expand(False)
+        self._check(self._lib.blk_puct_backup(C.byref(self.forest), self._stream()))
+        self.launches += 2
+
+    def advance(self, actions: torch.Tensor) -> None:
+        """Make the child under ``actions[t]`` the root of tree t (``-1`` leaves a tree where it is)."""
+        acts = actions.to(torch.int32).contiguous()
+        self._check(self._lib.blk_puct_advance(C.byref(self.forest), acts.data_ptr(), self._stream()))
+        self._step_and_expand(True)
+
+    # ---- results (host side; synchronises) ---------------------------------------------------------------------------
+    def check(self) -> None:
+        c = self.t["counters"].cpu().numpy()
+        if c[2]:
+            raise _lib.EngineError("GpuPuct capacity overflow (nodes / edges / depth): enlarge the forest")
+        if c[3]:
+            raise _lib.EngineError("GpuPuct produced an illegal action")
+
+    def scores(self) -> np.ndarray:
+        return self.t["scores"].cpu().numpy()
+
+    def root_states(self) -> torch.Tensor:
+        return self.pool.index_select(0, self.t["node_state"].index_select(0, self.t["root"].long()).long())
+
+    def root_stats(self):
+        """Per tree: (action ids, N, Q, P) of the root's edges as NumPy arrays."""
+        self.check()
+        root = self.t["root"].long()
+        e0 = self.t["node_edge0"].index_select(0, root).cpu().numpy()
+        n = self.t["node_nedge"].index_select(0, root).cpu().numpy()
+        n = np.where(e0 < 0, 0, n)
+        idx = np.concatenate([np.arange(a, a + b) for a, b in zip(e0, n)]) if n.sum() else np.zeros(0, np.int64)
+        di = torch.as_tensor(idx, device=root.device, dtype=torch.long)
+        cols = [self.t[k].index_select(0, di).cpu().numpy() for k in ("edge_action", "edge_n", "edge_q", "edge_p")]
+        split = np.cumsum(n)[:-1]
+        return [tuple(np.split(c, split)[t] for c in cols) for t in range(self.B)]
+
+    def best_actions(self) -> np.ndarray:
+        """Most visited root action per tree, first maximum (players/mcts_player.py:19-20); -1 for finished games."""
+        return np.array([int(a[int(np.argmax(n))]) if len(a) else -1 for a, n, _, _ in self.root_stats()], dtype=np.int32)

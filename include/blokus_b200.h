@@ -141,6 +141,62 @@ int blk_game_ended(blk_engine *h, const uint32_t *state, uint8_t *flags, float *
  * blokus_rl/players/random_player.py:11-17 repeated to the end of the game). */
 int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Device-resident PUCT forest (blokus_rl/alphazero/mcts.py:13-71 for B searches in lockstep).  All arrays are
+ * caller-owned DEVICE memory; one simulation = blk_puct_select -> blk_step on the requested transitions ->
+ * evaluator -> blk_puct_expand -> blk_puct_backup, without any host synchronisation.
+ * --------------------------------------------------------------------------------------------------------- */
+enum { BLK_PUCT_TERMINAL = 0, BLK_PUCT_NEED_EVAL = 1, BLK_PUCT_NEED_STEP = 2 };
+
+typedef struct {
+    int32_t num_trees, num_players, num_actions;
+    int32_t mask_stride;          /* bytes per byte-mask row (engine mask_bytes) */
+    int32_t node_capacity, edge_capacity, max_depth;
+    int32_t *node_edge0;          /* [nodes] first edge, -1 = not expanded */
+    int32_t *node_nedge;          /* [nodes] */
+    int32_t *node_state;          /* [nodes] slot of the node's state in the caller's state pool */
+    int8_t *node_mover;           /* [nodes] player to move */
+    int8_t *node_terminal;        /* [nodes] 1 = the game is over here */
+    double *node_term_value;      /* [nodes][P] 3/1/-1 vector of terminal nodes */
+    int32_t *edge_action;         /* [edges] action id (ascending within a node) */
+    int32_t *edge_child;          /* [edges] child node, -1 = not opened */
+    double *edge_n, *edge_q, *edge_p;   /* [edges] visit count, running mean, prior (mcts.py:67-70) */
+    int32_t *root;                /* [B] */
+    int32_t *path;                /* [B][max_depth] edges of the current simulation */
+    int32_t *path_len;            /* [B] */
+    int32_t *status;              /* [B] BLK_PUCT_* of the current simulation */
+    int32_t *leaf_node;           /* [B] node reached, or parent of the edge to open */
+    int32_t *leaf_edge;           /* [B] edge to open or -1 */
+    int32_t *src_slot;            /* [B] state slot blk_step must read for this tree */
+    int32_t *step_action;         /* [B] action for blk_step (BLK_ACTION_NONE: evaluate the state as it is) */
+    double *scores;               /* [B][P] score vector of the current simulation */
+    int32_t *counters;            /* [4] nodes used, edges used, capacity overflow flag, illegal-action flag */
+} blk_puct_forest;
+
+typedef struct {
+    int32_t new_slot_base;        /* pool slot of tree 0's new state; tree t uses new_slot_base + t */
+    int32_t state_words, meta_word;   /* engine state_words and the index of the meta word (P*N + P) */
+    int32_t attach_only;          /* 1: only create the requested child nodes and make them the roots (blk_puct_advance) */
+    const uint32_t *new_states;   /* [B][state_words] */
+    const uint8_t *mask;          /* [B][mask_stride] */
+    const uint8_t *flags;         /* [B] */
+    const float *terminal;        /* [B][P] */
+    const void *prior;            /* [B][prior_stride] or NULL */
+    int32_t prior_dtype;          /* 0 uniform over the legal actions (DumbNet), 1 float32, 2 float64 */
+    int64_t prior_stride;
+    const double *value;          /* [B][P] or NULL (zeros) */
+} blk_puct_expand_args;
+
+const char *blk_puct_last_error(void);
+/* MCTS.simulate, selection half: mcts.py:39-52 for every tree, down to a leaf / unopened edge / terminal node. */
+int blk_puct_select(const blk_puct_forest *f, double cpuct, int32_t epsilon_fix, void *stream);
+/* MCTS.simulate, expansion half: mcts.py:59-71 (winners / valid moves / nn.predict results become nodes + edges). */
+int blk_puct_expand(const blk_puct_forest *f, const blk_puct_expand_args *args, void *stream);
+/* MCTS.simulate, backup half: mcts.py:53-57 along the recorded path. */
+int blk_puct_backup(const blk_puct_forest *f, void *stream);
+/* After a real move: the child under `actions[t]` becomes the root (tree reuse, players/mcts_player.py:15-22). */
+int blk_puct_advance(const blk_puct_forest *f, const int32_t *actions, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
