@@ -322,6 +322,19 @@ def extra_workloads(eng, torch):
             eng.observe(leaves, out=obs)
         sec = timed(expand, 20)
         extra[f"leaf_expansions_per_s_B{B}"] = B / sec
+    # device-resident PUCT forest (config/mcts_blokus.yml player: MCTS with the uniform DumbNet prior), B trees in lockstep
+    from blokus_rl_b200.gpu_puct import GpuPuct
+    B, sims = 4096, 50
+    roots = eng.new_states(B)
+    o = eng.step(roots, None, mask=None, sample=True, seed=5)
+    for _ in range(24):
+        o = eng.step(roots, o.next_action, mask=None, sample=True, seed=5)
+    search = GpuPuct(eng, num_trees=B, max_simulations=2 * sims + 4, mean_edges_per_node=420)
+    search.set_roots(roots)
+    sec = timed(search.simulate, sims)
+    search.check()
+    extra["mcts_simulations_per_s"] = B / sec
+    extra["mcts_workload"] = f"{B} PUCT searches in lockstep from 24-ply roots, uniform prior (DumbNet), tree on the GPU (blk_puct_*)"
     return extra
 
 

@@ -69,6 +69,59 @@ def self_play_batched(engine, evaluator=None, num_games: int = 8, num_mcts_sims:
     return data, stats
 
 
+def self_play_gpu(engine, evaluator=None, num_games: int = 256, num_mcts_sims: int = 25, cpuct: float = 1.0,
+                  temperature: float = 1.0, dirichlet_alpha: float = 1.0, dirichlet_weight: float = 0.25,
+                  rng: np.random.Generator | None = None, max_plies: int = 4 * 21 + 1):
+    """Same contract as :func:`self_play_batched`, with the search trees resident on the GPU
+    (:class:`blokus_rl_b200.gpu_puct.GpuPuct`): the host only samples one move per game per ply."""
+    from .gpu_puct import GpuPuct
+    rng = rng or np.random.default_rng()
+    A, P = engine.num_actions, engine.num_players
+    search = GpuPuct(engine, evaluator or UniformEvaluator(), num_trees=num_games,
+                     max_simulations=(num_mcts_sims + 1) * max_plies + 2)
+    search.set_roots(engine.new_states(num_games))
+    data: list[list] = [[] for _ in range(num_games)]
+    done = np.zeros(num_games, bool)
+    first = True
+    plies = 0
+    while not done.all() and plies < max_plies:
+        for _ in range(num_mcts_sims):
+            search.simulate(cpuct)
+        roots = search.root_states()
+        obs = engine.observe(roots).cpu().numpy()
+        stats = search.root_stats()
+        acts = np.full(num_games, -1, np.int32)
+        for t in range(num_games):
+            if done[t]:
+                continue
+            ids, n, _, _ = stats[t]
+            if temperature == 0:
+                dist = np.zeros(len(ids)); dist[int(np.argmax(n))] = 1.0
+            else:
+                dist = np.power(n, 1.0 / temperature)
+            dist = dist / dist.sum() if dist.sum() > 0 else np.full(len(ids), 1.0 / len(ids))
+            if first:
+                dist = dist * (1 - dirichlet_weight) + rng.dirichlet(dirichlet_alpha * np.ones(len(ids), np.float32)) * dirichlet_weight
+            prob = dist.astype(np.float32)
+            mask = np.zeros(A, dtype=np.float64)
+            mask[ids] = 1
+            data[t].append([obs[t], mask, prob, None])
+            p64 = prob.astype(np.float64)
+            acts[t] = int(ids[rng.choice(len(ids), p=p64 / p64.sum())])
+        first = False
+        search.advance(torch.as_tensor(acts, device=engine.device))
+        flags, term, _ = engine.game_ended(search.root_states())
+        ended = (flags.cpu().numpy() & 1).astype(bool) & ~done
+        term = term.cpu().numpy().astype(np.float64)
+        for t in np.flatnonzero(ended):
+            for ex in data[t]:
+                ex[-1] = term[t]
+        done |= ended
+        plies += 1
+    search.check()
+    return data, {"games": num_games, "examples": sum(len(d) for d in data), "launches": search.launches, "plies": plies}
+
+
 def save_examples(examples_per_game, save_dir, iteration: int = 0, prefix: str = "checkpoint") -> list[Path]:
     """One pickle per game under ``save_dir/iteration_{k}/`` (reference layout: trainer.py:287-292)."""
     out_dir = Path(save_dir) / f"iteration_{iteration}"

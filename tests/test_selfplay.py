@@ -58,6 +58,17 @@ def test_selfplay_examples_gpu(tmp_path, engine7):
 
 
 @pytest.mark.gpu
+def test_selfplay_on_the_gpu_forest(tmp_path, engine7):
+    from blokus_rl_b200.selfplay import self_play_gpu
+    data, stats = self_play_gpu(engine7, num_games=32, num_mcts_sims=6, rng=np.random.default_rng(1))
+    assert stats["examples"] == sum(len(d) for d in data) and all(2 <= len(g) <= 42 for g in data)
+    for game in data[:4]:
+        for obs, mask, prob, scores in game:
+            assert obs.shape == (4, 7, 7) and len(prob) == int(mask.sum()) and abs(prob.sum() - 1) < 1e-5
+            assert scores is not None and set(np.unique(scores)) <= {-1.0, 1.0, 3.0}
+
+
+@pytest.mark.gpu
 def test_arena_gpu(engine7, engine20):
     _check_arena(engine7)
     from blokus_rl_b200.selfplay import RandomSeat, RolloutSeat, play_match_batched
