@@ -66,3 +66,16 @@ def test_product_package_never_imports_oracle():
     for f in (ROOT / "blokus_rl_b200").rglob("*.py"):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No .so -> EngineError naming the build command; never a silent fallback."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from blokus_rl_b200 import _lib\n"
+            "try:\n    _lib.load()\nexcept _lib.EngineError as e:\n    print('LOUD', 'no CPU fallback' in str(e) or 'missing' in str(e))\n" % str(ROOT))
+    env = dict(os.environ, BLOKUS_B200_LIB=str(tmp_path / "nope.so"))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert "LOUD True" in out.stdout, out.stdout + out.stderr
