@@ -9,6 +9,7 @@
 //   a7 action table    -> build_tables() (host)     rollouts (new)    -> rollout_kernel
 //
 // No tensor cores: nothing here is a contraction.  No CPU fallback: every entry point needs the GPU.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -99,6 +100,68 @@ __global__ void observe_kernel(const uint32_t *__restrict__ state, float *__rest
     } else {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) obs[e0 + k] = v[k];
+    }
+}
+
+// Warp-per-env streaming variants for board sizes with N*N % 16 == 0 (20x20: every index division is by a constant).
+// The env's row words sit in shared memory; a 16-entry LUT turns 4 occupancy bits into one float4.
+template <int kN, int kP>
+__global__ void __launch_bounds__(256) observe_rows_kernel(const uint32_t *__restrict__ state, float *__restrict__ obs,
+                                                          int64_t n) {
+    constexpr int kQuadsPerPlane = kN * kN / 4, kQuadsPerRow = kN / 4, kQuads = 2 * kP * kQuadsPerPlane;
+    constexpr int kSw = kP * kN + kP + 4;
+    __shared__ float4 s_lut[16];
+    __shared__ uint32_t s_rows[8][kP * kN + 1];
+    if (threadIdx.x < 16)
+        s_lut[threadIdx.x] = make_float4(threadIdx.x & 1 ? 1.f : 0.f, threadIdx.x & 2 ? 1.f : 0.f,
+                                         threadIdx.x & 4 ? 1.f : 0.f, threadIdx.x & 8 ? 1.f : 0.f);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *rows = s_rows[warp];
+    for (int64_t env = static_cast<int64_t>(blockIdx.x) * 8 + warp; env < n; env += static_cast<int64_t>(gridDim.x) * 8) {
+        const uint32_t *s = state + env * kSw;
+        for (int i = lane; i < kP * kN; i += 32) rows[i] = __ldg(s + i);
+        if (lane == 0) rows[kP * kN] = __ldg(s + kP * kN + kP) & 15u;          // mover
+        __syncwarp();
+        const int mover = rows[kP * kN];
+        float4 *out = reinterpret_cast<float4 *>(obs + env * (4 * kQuads));
+#pragma unroll 5
+        for (int j = lane; j < kQuads; j += 32) {
+            const int plane = j / kQuadsPerPlane, w = j - plane * kQuadsPerPlane;
+            const int y = w / kQuadsPerRow, x0 = (w - y * kQuadsPerRow) * 4;
+            float4 v;
+            if (plane < kP) v = s_lut[(rows[plane * kN + y] >> x0) & 15u];
+            else v = s_lut[(plane - kP == mover) ? 15 : 0];
+            __stcs(out + j, v);
+        }
+        __syncwarp();
+    }
+}
+
+template <int kN, int kP>
+__global__ void __launch_bounds__(256) contents_rows_kernel(const uint32_t *__restrict__ state, uint8_t *__restrict__ board,
+                                                           int64_t n) {
+    constexpr int kChunks = kN * kN / 16, kSw = kP * kN + kP + 4;
+    __shared__ uint32_t s_rows[8][kP * kN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *rows = s_rows[warp];
+    for (int64_t env = static_cast<int64_t>(blockIdx.x) * 8 + warp; env < n; env += static_cast<int64_t>(gridDim.x) * 8) {
+        const uint32_t *s = state + env * kSw;
+        for (int i = lane; i < kP * kN; i += 32) rows[i] = __ldg(s + i);
+        __syncwarp();
+        if (lane < kChunks) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int cell = 16 * lane + i, y = cell / kN, x = cell - y * kN;
+                uint32_t c = 0u;
+#pragma unroll
+                for (int q = 0; q < kP; ++q) c |= ((rows[q * kN + y] >> x) & 1u) * static_cast<uint32_t>(q + 1);
+                w[i >> 2] |= c << (8 * (i & 3));
+            }
+            reinterpret_cast<uint4 *>(board + env * (kN * kN))[lane] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncwarp();
     }
 }
 
@@ -407,7 +470,13 @@ int blk_observe(blk_engine *h, const uint32_t *state, float *obs, int64_t n, voi
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int64_t elems = n * 2 * h->g.P * h->g.N * h->g.N;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((h->g.N * h->g.N) % 4 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+    const int wgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
+    if (aligned && h->g.N == 20 && h->g.P == 4) {
+        observe_rows_kernel<20, 4><<<wgrid, 256, 0, st>>>(state, obs, n);
+    } else if (aligned && h->g.N == 20 && h->g.P == 2) {
+        observe_rows_kernel<20, 2><<<wgrid, 256, 0, st>>>(state, obs, n);
+    } else if ((h->g.N * h->g.N) % 4 == 0 && aligned) {
         const int64_t thr = elems / 4;
         observe_kernel<4><<<static_cast<unsigned>((thr + 255) / 256), 256, 0, st>>>(state, obs, n, h->g);
     } else {
@@ -422,7 +491,12 @@ int blk_board_contents(blk_engine *h, const uint32_t *state, uint8_t *board, int
     if (n == 0) return BLK_OK;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int64_t elems = n * h->g.N * h->g.N;
-    contents_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(state, board, n, h->g);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
+    const bool aligned = (reinterpret_cast<uintptr_t>(board) & 15) == 0;
+    if (aligned && h->g.N == 20 && h->g.P == 4) contents_rows_kernel<20, 4><<<wgrid, 256, 0, st>>>(state, board, n);
+    else if (aligned && h->g.N == 20 && h->g.P == 2) contents_rows_kernel<20, 2><<<wgrid, 256, 0, st>>>(state, board, n);
+    else contents_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, st>>>(state, board, n, h->g);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
 }
