@@ -726,13 +726,21 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(co
         int cand = static_cast<int>(e.meta & 15u);
         cand = cand == 0 ? P - 1 : cand - 1;
         int tries = 1;
+        uint32_t stuck = 0u;
 #pragma unroll 1
         while (!over) {
             cand = (cand + 1 == P) ? 0 : cand + 1;
-            uint32_t fr0, dg0;
-            prep_rows(e, cand, g, lane, fr0, dg0);
-            const uint32_t acc = eval_fields<true>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
-            if (!__any_sync(kAllLanes, acc != 0u)) {
+            bool has = false;
+            if (!((stuck >> cand) & 1u)) {
+                uint32_t fr0, dg0;
+                prep_rows(e, cand, g, lane, fr0, dg0);
+                const uint32_t acc = eval_fields<true>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
+                has = __any_sync(kAllLanes, acc != 0u);
+                // a player without a move never gets one back (others only take cells away, and it places nothing
+                // itself), so it is not evaluated again for the rest of the playout
+                if (!has) stuck |= 1u << cand;
+            }
+            if (!has) {
                 if (--tries > 0) continue;
                 e.meta |= 1u << 4;
                 over = true;
