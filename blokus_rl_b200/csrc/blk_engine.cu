@@ -283,8 +283,7 @@ int build_tables(blk_engine *h) {
         uint32_t info = static_cast<uint32_t>(r.piece) | (static_cast<uint32_t>(r.h) << 8) |
                         (static_cast<uint32_t>(r.w) << 12) | (static_cast<uint32_t>(r.n) << 16);
         uint32_t cells = 0;
-        for (int c = 0; c < 5; ++c)
-            cells |= (static_cast<uint32_t>(r.yx[2 * c]) | (static_cast<uint32_t>(r.yx[2 * c + 1]) << 3)) << (6 * c);
+        for (int c = 0; c < r.n; ++c) cells |= 1u << (5 * r.yx[2 * c] + r.yx[2 * c + 1]);   // row patterns, 5 bits per row
         memcpy(blob.data() + t.off_oinfo + 4 * o, &info, 4);
         memcpy(blob.data() + t.off_ocells + 4 * o, &cells, 4);
     }

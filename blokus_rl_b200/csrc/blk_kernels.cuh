@@ -58,7 +58,7 @@ constexpr int kOffLut = 0, kOffWdesc = 2048;   // fixed offsets inside the table
 struct TableLayout {
     int off_obase;   // int32[92]   first action id of each orientation (+ sentinel A)
     int off_oinfo;   // uint32[92]  piece | h<<8 | w<<12 | ncells<<16
-    int off_ocells;  // uint32[92]  5 x (dy:3, dx:3)
+    int off_ocells;  // uint32[92]  footprint as 5 row patterns of 5 bits: bits [5r, 5r+5) = columns of row r
     int off_foff;    // uint16[nf+1] bit offset (= first action id) of each field, sentinel 0xFFFF
     int off_wsrc;    // uint16[mw]  first field intersecting mask word g
     int off_fbase;   // uint16[92]  first field index of each orientation
@@ -432,11 +432,8 @@ __device__ __forceinline__ bool decode_action(int act, const SmemTables &tb, con
     const int rem = act - tb.obase[o];
     const int ay = rem / W;
     const int ax = rem - ay * W;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        const int dy = (cells >> (6 * c)) & 7, dx = (cells >> (6 * c + 3)) & 7;
-        if (c < ncells && ay + dy == lane) pm |= 1u << (ax + dx);
-    }
+    const int d = lane - ay;                                   // this lane's row of the footprint, if any
+    if (d >= 0 && d < 5) pm = ((cells >> (5 * d)) & 31u) << ax;
     return true;
 }
 
@@ -448,12 +445,8 @@ __device__ __forceinline__ void decode_field(int fsel, int bit, const SmemTables
     const uint32_t oi = tb.oinfo[o], cells = tb.ocells[o];
     piece = oi & 31;
     ncells = (oi >> 16) & 15;
-    pm = 0u;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        const int dy = (cells >> (6 * c)) & 7, dx = (cells >> (6 * c + 3)) & 7;
-        if (c < ncells && ay + dy == lane) pm |= 1u << (bit + dx);
-    }
+    const int d = lane - ay;
+    pm = (d >= 0 && d < 5) ? ((cells >> (5 * d)) & 31u) << bit : 0u;
 }
 
 __device__ __forceinline__ void apply_placement(EnvRegs &e, int p, uint32_t pm, int piece, int ncells) {
