@@ -21,7 +21,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "blk_last_error", "blk_abi_version", "blk_create", "blk_destroy", "blk_get_info", "blk_action_to_cells",
     "blk_reset", "blk_step", "blk_observe", "blk_board_contents", "blk_game_ended", "blk_rollout",
-    "blk_puct_last_error", "blk_puct_select", "blk_puct_expand", "blk_puct_backup", "blk_puct_advance",
+    "blk_puct_last_error", "blk_puct_select", "blk_puct_expand", "blk_puct_backup", "blk_puct_best", "blk_puct_advance",
 )
 
 
@@ -102,6 +102,7 @@ def load() -> C.CDLL:
     lib.blk_puct_select.argtypes = [C.POINTER(BlkPuctForest), C.c_double, C.c_int32, C.c_void_p]
     lib.blk_puct_expand.argtypes = [C.POINTER(BlkPuctForest), C.POINTER(BlkPuctExpandArgs), C.c_void_p]
     lib.blk_puct_backup.argtypes = [C.POINTER(BlkPuctForest), C.c_void_p]
+    lib.blk_puct_best.argtypes = [C.POINTER(BlkPuctForest), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.blk_puct_advance.argtypes = [C.POINTER(BlkPuctForest), C.c_void_p, C.c_void_p]
     if lib.blk_abi_version() != ABI_VERSION:
         raise EngineError("libblokus_b200.so ABI version mismatch; rebuild")

@@ -229,6 +229,31 @@ __global__ void puct_advance_kernel(blk_puct_forest f, const int32_t *actions) {
     else { f.status[t] = BLK_PUCT_NEED_STEP; f.leaf_edge[t] = found; f.step_action[t] = act; }
 }
 
+// most visited root action per tree (first maximum, players/mcts_player.py:19-20); -1 when the root has no edges
+__global__ void puct_best_kernel(blk_puct_forest f, int32_t *best_action, double *best_visits) {
+    const int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= f.num_trees) return;
+    const int node = f.root[t];
+    const int e0 = f.node_edge0[node], n = e0 < 0 ? 0 : f.node_nedge[node];
+    double best = -1.0;
+    int besti = 0x7fffffff;
+    for (int i = lane; i < n; i += 32) {
+        const double v = f.edge_n[e0 + i];
+        if (v > best) { best = v; besti = i; }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const double ob = __shfl_xor_sync(kAll, best, d);
+        const int oi = __shfl_xor_sync(kAll, besti, d);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (lane == 0) {
+        best_action[t] = n > 0 ? f.edge_action[e0 + besti] : -1;
+        if (best_visits != nullptr) best_visits[t] = n > 0 ? best : 0.0;
+    }
+}
+
 thread_local std::string g_puct_err;
 int puct_fail(const char *msg) { g_puct_err = msg; return BLK_ERR_ARG; }
 int puct_launch_check() {
@@ -270,6 +295,14 @@ int blk_puct_backup(const blk_puct_forest *f, void *stream) {
     if (!f) return puct_fail("null argument");
     if (f->num_trees == 0) return BLK_OK;
     puct_backup_kernel<<<(f->num_trees + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*f);
+    return puct_launch_check();
+}
+
+int blk_puct_best(const blk_puct_forest *f, int32_t *best_action, double *best_visits, void *stream) {
+    if (!f || !best_action) return puct_fail("null argument");
+    if (f->num_trees == 0) return BLK_OK;
+    const int grid = (f->num_trees + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    puct_best_kernel<<<grid, kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(*f, best_action, best_visits);
     return puct_launch_check();
 }
 

@@ -147,9 +147,15 @@ class GpuPuct:
         idx = np.concatenate([np.arange(a, a + b) for a, b in zip(e0, n)]) if n.sum() else np.zeros(0, np.int64)
         di = torch.as_tensor(idx, device=root.device, dtype=torch.long)
         cols = [self.t[k].index_select(0, di).cpu().numpy() for k in ("edge_action", "edge_n", "edge_q", "edge_p")]
-        split = np.cumsum(n)[:-1]
-        return [tuple(np.split(c, split)[t] for c in cols) for t in range(self.B)]
+        parts = [np.split(c, np.cumsum(n)[:-1]) for c in cols]
+        return [tuple(col[t] for col in parts) for t in range(self.B)]
+
+    def best_actions_device(self) -> torch.Tensor:
+        """Most visited root action per tree, first maximum (players/mcts_player.py:19-20); -1 for finished games.
+        Stays on the device and does not synchronise: feed it straight to :meth:`advance` / ``engine.step``."""
+        out = torch.empty(self.B, dtype=torch.int32, device=self.eng.device)
+        self._check(self._lib.blk_puct_best(C.byref(self.forest), out.data_ptr(), None, self._stream()))
+        return out
 
     def best_actions(self) -> np.ndarray:
-        """Most visited root action per tree, first maximum (players/mcts_player.py:19-20); -1 for finished games."""
-        return np.array([int(a[int(np.argmax(n))]) if len(a) else -1 for a, n, _, _ in self.root_stats()], dtype=np.int32)
+        return self.best_actions_device().cpu().numpy()

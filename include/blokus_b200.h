@@ -194,6 +194,8 @@ int blk_puct_select(const blk_puct_forest *f, double cpuct, int32_t epsilon_fix,
 int blk_puct_expand(const blk_puct_forest *f, const blk_puct_expand_args *args, void *stream);
 /* MCTS.simulate, backup half: mcts.py:53-57 along the recorded path. */
 int blk_puct_backup(const blk_puct_forest *f, void *stream);
+/* MCTSPlayer's choice, players/mcts_player.py:19-20: most visited root action per tree (first maximum); device arrays [B]. */
+int blk_puct_best(const blk_puct_forest *f, int32_t *best_action, double *best_visits, void *stream);
 /* After a real move: the child under `actions[t]` becomes the root (tree reuse, players/mcts_player.py:15-22). */
 int blk_puct_advance(const blk_puct_forest *f, const int32_t *actions, void *stream);
 
