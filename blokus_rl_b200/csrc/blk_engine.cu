@@ -514,7 +514,8 @@ int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream) {
     if (!h || !args) return fail(BLK_ERR_ARG, "null argument");
     if (args->n_roots < 0 || args->per_root < 0) return fail(BLK_ERR_ARG, "negative count");
     if (args->n_roots == 0 || args->per_root == 0) return BLK_OK;
-    if (!args->roots || !args->final_scores) return fail(BLK_ERR_ARG, "roots / final_scores are required");
+    if (!args->roots) return fail(BLK_ERR_ARG, "roots are required");
+    if (args->stop_player < -1 || args->stop_player >= h->g.P) return fail(BLK_ERR_ARG, "stop_player out of range");
     if (args->action_log && args->log_stride < 4 * kPieces + 1) return fail(BLK_ERR_ARG, "log_stride must be >= 85");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     RParams rp;

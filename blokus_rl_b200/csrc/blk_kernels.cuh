@@ -741,6 +741,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(co
             }
             __syncwarp();
             e.meta = (e.meta & ~15u) | static_cast<uint32_t>(cand);
+            if (cand == a.stop_player) break;              // caller's turn: hand the state back
             // count legal actions: lane sums popcounts over its contiguous chunk of fields (field order = id order)
             int mine = 0;
             if (kN == 20) {                     // 1665 fields = 32 x 52 (+1 for lane 31): 13 conflict-free LDS.128 per lane
@@ -796,11 +797,12 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(co
         const float tval = terminal_value(e, g, lane, fscore);
         const uint32_t win = __ballot_sync(kAllLanes, lane < P && tval > 0.f);
         if (lane < P) {
-            a.final_scores[gid * P + lane] = static_cast<int16_t>(fscore);
-            if (a.value_sum != nullptr) atomicAdd(a.value_sum + root * P + lane, tval);
+            if (a.final_scores != nullptr) a.final_scores[gid * P + lane] = static_cast<int16_t>(fscore);
+            if (a.value_sum != nullptr && over) atomicAdd(a.value_sum + root * P + lane, tval);
         }
+        if (a.state_out != nullptr) env_store(e, a.state_out + gid * sw, g, lane);
         if (lane == 0) {
-            if (a.winners != nullptr) a.winners[gid] = static_cast<uint8_t>(win);
+            if (a.winners != nullptr) a.winners[gid] = over ? static_cast<uint8_t>(win) : 0;
             if (a.plies != nullptr) a.plies[gid] = nply;
             if (a.action_log != nullptr) a.action_log[gid * a.log_stride + min(nply, a.log_stride - 1)] = 0xFFFFu;
         }

@@ -228,7 +228,10 @@ class BlokusEngine:
 
     # ---- kernel family 4: uniform-random playouts to the end of the game ---------------------------------
     def rollout(self, roots: torch.Tensor, per_root: int, seed: int = 0, rollout_id_base: int = 0,
-                log_actions: bool = False) -> RolloutOut:
+                log_actions: bool = False, stop_player: int = -1, out_states: torch.Tensor | None = None) -> RolloutOut:
+        """Uniform-random playouts.  ``stop_player = q`` stops each playout as soon as it is player q's turn (or
+        the game is over) and ``out_states`` (may alias ``roots`` when ``per_root == 1``) receives the states
+        reached: this is how the gym adapter plays the random-bot opponents inside one ``step``."""
         self._check_states(roots)
         n, P, dev = roots.shape[0], self.num_players, self.device
         total = n * per_root
@@ -238,9 +241,13 @@ class BlokusEngine:
         plies = torch.empty((n, per_root), dtype=torch.int32, device=dev)
         log_stride = 88
         log = torch.empty((n, per_root, log_stride), dtype=torch.int16, device=dev) if log_actions else None
+        if out_states is not None and (out_states.dtype != torch.int32 or not out_states.is_contiguous()
+                                       or out_states.numel() != total * self.state_words):
+            raise ValueError("out_states must be a contiguous int32 [n * per_root, state_words] tensor")
         args = _lib.BlkRolloutArgs(n, roots.data_ptr(), per_root, seed & 0xFFFFFFFFFFFFFFFF, rollout_id_base & 0xFFFFFFFF,
                                    final_scores.data_ptr(), winners.data_ptr(), value_sum.data_ptr(),
-                                   None if log is None else log.data_ptr(), log_stride, plies.data_ptr())
+                                   None if log is None else log.data_ptr(), log_stride, plies.data_ptr(),
+                                   int(stop_player), None if out_states is None else out_states.data_ptr())
         if total:
             _lib.check(self._lib.blk_rollout(self._h, C.byref(args), self._stream()))
         return RolloutOut(final_scores, winners, value_sum, plies, log)

@@ -65,16 +65,14 @@ class BlokusVectorEnv:
     def _done(self):
         return ((self.states[:, self._meta] >> 4) & 1).bool()
 
-    def _play_opponents(self, out, reward, finished):
-        """Step the random bots until it is the agent's turn (or the game is over) in every env."""
-        for _ in range(self.P * 22):                     # a bot can move many times in a row when others are stuck
-            pending = (self._mover() != self.agent) & ~self._done()
-            if not bool(pending.any()):
-                break
-            acts = torch.where(pending, out.next_action, torch.full_like(out.next_action, -1))
-            self._epoch += 1
-            out = self.eng.step(self.states, acts, mask="bytes", sample=True, seed=self.seed + self._epoch)
-        return out
+    def _play_opponents(self):
+        """Random bots move (one rollout launch, no host sync) until it is the agent's turn or the game is over."""
+        self._epoch += 1
+        self.eng.rollout(self.states, 1, seed=self.seed + self._epoch, stop_player=self.agent, out_states=self.states)
+
+    def _refresh_mask(self):
+        self.action_mask = self.eng.step(self.states, None, mask="bytes", want_count=False, want_terminal=False,
+                                         want_scores=False).mask
 
     def _obs(self):
         return self.eng.board_contents(self.states)
@@ -86,42 +84,38 @@ class BlokusVectorEnv:
         self.states = self.eng.new_states(self.num_envs)
         self._ep_len.zero_()
         self._ep_ret.zero_()
-        self._epoch += 1
-        out = self.eng.step(self.states, None, mask="bytes", sample=True, seed=self.seed + self._epoch)
         if self.agent != 0:
-            out = self._play_opponents(out, None, None)
-        self.action_mask = out.mask
+            self._play_opponents()
+        self._refresh_mask()
         return self._obs().cpu().numpy().astype(np.float32), {}
 
-    def step_device(self, actions: torch.Tensor):
+    def step_device(self, actions: torch.Tensor, check: bool = True):
         """Device-side step: int32 CUDA actions in; (obs uint8 [E,N,N], reward f32 [E], terminated bool [E],
-        final episode (returns, lengths) for the envs that finished) out, all on the device."""
+        (episode returns, episode lengths, final observations) for the envs that finished) out, all on the
+        device.  With ``check=False`` nothing synchronises with the host (illegal actions then leave their env
+        unchanged, as ``blk_step`` defines)."""
         eng = self.eng
-        self._epoch += 1
-        out = eng.step(self.states, actions.to(torch.int32).contiguous(), mask="bytes", sample=True,
-                       seed=self.seed + self._epoch)
-        if bool((out.flags & 2).any()):
+        out = eng.step(self.states, actions.to(torch.int32).contiguous(), mask=None, want_count=False,
+                       want_terminal=False, want_scores=False)
+        if check and bool((out.flags & 2).any()):
             raise ValueError("illegal action passed to BlokusVectorEnv.step")
-        out = self._play_opponents(out, None, None)
-        done = self._done()
-        _, term, _ = eng.game_ended(self.states)
+        self._play_opponents()
+        flags, term, _ = eng.game_ended(self.states)
+        done = (flags & 1).bool()
         mine = term[:, self.agent]
         reward = torch.where(done, torch.where(mine == 3, 1.0, torch.where(mine == 1, 0.0, -1.0)), 0.0).float()
         self._ep_len += 1
         self._ep_ret += reward
         fin_ret, fin_len = self._ep_ret.clone(), self._ep_len.clone()
-        final_obs = None
-        if bool(done.any()):                             # gymnasium-0.29 autoreset: return the NEW episode's obs
-            final_obs = self._obs()
-            fresh = eng.new_states(self.num_envs)
-            self.states = torch.where(done[:, None], fresh, self.states).contiguous()
-            self._ep_len = torch.where(done, torch.zeros_like(self._ep_len), self._ep_len)
-            self._ep_ret = torch.where(done, torch.zeros_like(self._ep_ret), self._ep_ret)
-            self._epoch += 1
-            out = eng.step(self.states, None, mask="bytes", sample=True, seed=self.seed + self._epoch)
-            if self.agent != 0:
-                out = self._play_opponents(out, None, None)
-        self.action_mask = out.mask
+        final_obs = self._obs()
+        # gymnasium-0.29 autoreset: finished envs restart at once and return the NEW episode's first observation
+        fresh = eng.new_states(self.num_envs)
+        self.states = torch.where(done[:, None], fresh, self.states).contiguous()
+        self._ep_len = torch.where(done, torch.zeros_like(self._ep_len), self._ep_len)
+        self._ep_ret = torch.where(done, torch.zeros_like(self._ep_ret), self._ep_ret)
+        if self.agent != 0:
+            self._play_opponents()
+        self._refresh_mask()
         return self._obs(), reward, done, (fin_ret, fin_len, final_obs)
 
     def step(self, actions):

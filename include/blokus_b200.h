@@ -98,12 +98,15 @@ typedef struct {
     int32_t per_root;           /* playouts per root */
     uint64_t seed;              /* key = (seed_lo, seed_hi ^ game_index), game_index = rollout_id_base + root*per_root + j; ctr = (ply >> 2, game, 1, 0), word ply & 3 */
     uint32_t rollout_id_base;
-    int16_t *final_scores;      /* [n_roots*per_root][P] */
+    int16_t *final_scores;      /* nullable [n_roots*per_root][P] */
     uint8_t *winners;           /* nullable [n_roots*per_root] bitmask of winners */
     float *value_sum;           /* nullable [n_roots][P]; sum over playouts of the 3/1/-1 terminal vector (atomicAdd; caller zeroes) */
     uint16_t *action_log;       /* nullable [n_roots*per_root][log_stride]; 0xFFFF terminated */
     int32_t log_stride;         /* >= 4*21+1 when action_log != NULL */
     int32_t *plies;             /* nullable [n_roots*per_root] plies played */
+    int32_t stop_player;        /* -1: play to the end of the game; q: stop as soon as it is player q's turn (random-bot
+                                   opponents inside a gym step: docs/README.md:47-51 of the reference) */
+    uint32_t *state_out;        /* nullable [n_roots*per_root][state_words]: the state each playout stopped in */
 } blk_rollout_args;
 
 const char *blk_last_error(void);

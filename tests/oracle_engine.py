@@ -95,7 +95,7 @@ class OracleEngine:
         scores = torch.from_numpy(np.stack([self.orc.final_scores(s)[: self.num_players] for s in sts]))
         return flags, term, scores
 
-    def rollout(self, roots, per_root, seed=0, rollout_id_base=0, log_actions=False):
+    def rollout(self, roots, per_root, seed=0, rollout_id_base=0, log_actions=False, stop_player=-1, out_states=None):
         orc, P = self.orc, self.num_players
         sts = self._unpack(roots)
         n = len(sts)
@@ -103,16 +103,21 @@ class OracleEngine:
         win = np.zeros((n, per_root), np.uint8)
         vs = np.zeros((n, P), np.float32)
         plies = np.zeros((n, per_root), np.int32)
+        finals = []
         for r, root in enumerate(sts):
             for j in range(per_root):
                 s = orc.copy(root)
                 gid = rollout_id_base + r * per_root + j
                 k = 0
-                while not orc.field(s, "done"):
+                while not orc.field(s, "done") and orc.field(s, "mover") != stop_player:
                     orc.step(s, orc.sample_action(s, seed, gid, stream=1), fast=True)
                     k += 1
                 fs[r, j] = orc.final_scores(s)[:P]
-                win[r, j] = orc.winners(s)
-                vs[r] += orc.terminal_values(s)
+                if orc.field(s, "done"):
+                    win[r, j] = orc.winners(s)
+                    vs[r] += orc.terminal_values(s)
                 plies[r, j] = k
+                finals.append(s)
+        if out_states is not None:
+            self._pack(finals, out_states.view(-1, self.state_words))
         return RolloutOut(torch.from_numpy(fs), torch.from_numpy(win), torch.from_numpy(vs), torch.from_numpy(plies), None)

@@ -35,7 +35,7 @@ def test_abi_version_and_struct_sizes(lib):
     from blokus_rl_b200 import _lib
     assert lib.blk_abi_version() == 1
     assert C.sizeof(_lib.BlkConfig) == 16 and C.sizeof(_lib.BlkInfo) == 44
-    assert C.sizeof(_lib.BlkStepArgs) == 112 and C.sizeof(_lib.BlkRolloutArgs) == 88
+    assert C.sizeof(_lib.BlkStepArgs) == 112 and C.sizeof(_lib.BlkRolloutArgs) == 104
 
 
 def test_no_cpu_fallback(lib):
