@@ -28,6 +28,8 @@ struct OrientRow {
     int8_t piece, local, h, w, n;
     int8_t yx[10];
 };
+#define BLK_BASE(...)
+#define BLK_ORIENT_B(...)
 #define BLK_PIECE_BEGIN(p)
 #define BLK_ORIENT(...)
 #define BLK_PIECE_ELSE(p)
@@ -38,6 +40,8 @@ struct OrientRow {
 const OrientRow kOrient[kOrients] = {
 #include "blk_orient.inc"
 };
+#undef BLK_BASE
+#undef BLK_ORIENT_B
 #undef BLK_PIECE_BEGIN
 #undef BLK_ORIENT
 #undef BLK_PIECE_ELSE

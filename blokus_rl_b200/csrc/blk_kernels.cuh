@@ -338,6 +338,17 @@ __device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint
     uint32_t anyacc = 0u;
     const int np1 = N + 1;
     uint32_t *fldp = fld + lane;
+    // AND / OR over the cells of five base trominoes, shared by the 75 footprints that contain one of them
+    uint32_t base_and[5], base_or[5];
+#define BLK_BASE(b, y0, x0, y1, x1, y2, x2)                  \
+    base_and[b] = fs[y0][x0] & fs[y1][x1] & fs[y2][x2];       \
+    base_or[b] = ds[y0][x0] | ds[y1][x1] | ds[y2][x2];
+#define BLK_ORIENT_B(o, p, h, w, n, hsum, b, y0, x0, y1, x1)                                            \
+    {                                                                                                  \
+        const uint32_t f_ = (base_and[b] & fs[y0][x0] & fs[y1][x1]) & (base_or[b] | ds[y0][x0] | ds[y1][x1]); \
+        anyacc |= f_;                                                                                  \
+        if (kStage && ok[h]) fldp[(o) * np1 - (hsum)] = f_;                                            \
+    }
 #define BLK_PIECE_BEGIN(p) if ((invc >> (p)) & 1u) {
 #define BLK_ORIENT(o, p, h, w, n, hsum, y0, x0, y1, x1, y2, x2, y3, x3, y4, x4)                        \
     {                                                                                                  \
@@ -353,6 +364,8 @@ __device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint
     if (ok[h]) fldp[(o) * np1 - (hsum)] = 0u;
 #define BLK_PIECE_END(p) }
 #include "blk_orient.inc"
+#undef BLK_BASE
+#undef BLK_ORIENT_B
 #undef BLK_PIECE_BEGIN
 #undef BLK_ORIENT
 #undef BLK_PIECE_ELSE
