@@ -318,7 +318,7 @@ __device__ __forceinline__ int final_score(const EnvRegs &e, int q, const Dims &
 // All 91 orientations against rows lane..lane+4 of the free / diagonal boards.  Stages one field per
 // (orientation, anchor row = lane) at fld[o*(N+1) - hsum(o) + lane] and returns this lane's OR of them.
 // Every (dy, dx) a 5-cell piece can reach satisfies dy + dx <= 4: 15 shifted copies of each board.
-template <bool kStage>
+template <bool kStage, bool kAny = true>
 __device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint32_t invc, uint32_t *fld, int N,
                                                 int lane) {
     uint32_t fs[5][5], ds[5][5];
@@ -346,7 +346,7 @@ __device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint
 #define BLK_ORIENT_B(o, p, h, w, n, hsum, b, y0, x0, y1, x1)                                            \
     {                                                                                                  \
         const uint32_t f_ = (base_and[b] & fs[y0][x0] & fs[y1][x1]) & (base_or[b] | ds[y0][x0] | ds[y1][x1]); \
-        anyacc |= f_;                                                                                  \
+        if (kAny) anyacc |= f_;                                                                        \
         if (kStage && ok[h]) fldp[(o) * np1 - (hsum)] = f_;                                            \
     }
 #define BLK_PIECE_BEGIN(p) if ((invc >> (p)) & 1u) {
@@ -354,7 +354,7 @@ __device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint
     {                                                                                                  \
         const uint32_t f_ = (fs[y0][x0] & fs[y1][x1] & fs[y2][x2] & fs[y3][x3] & fs[y4][x4]) &         \
                             (ds[y0][x0] | ds[y1][x1] | ds[y2][x2] | ds[y3][x3] | ds[y4][x4]);         \
-        anyacc |= f_;                                                                                  \
+        if (kAny) anyacc |= f_;                                                                        \
         if (kStage && ok[h]) fldp[(o) * np1 - (hsum)] = f_;                                            \
     }
 #define BLK_PIECE_ELSE(p) \
@@ -737,11 +737,27 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(co
         while (!over) {
             cand = (cand + 1 == P) ? 0 : cand + 1;
             bool has = false;
+            int mine = 0, incl = 0;
             if (!((stuck >> cand) & 1u)) {
                 uint32_t fr0, dg0;
                 prep_rows(e, cand, g, lane, fr0, dg0);
-                const uint32_t acc = eval_fields<true>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
-                has = __any_sync(kAllLanes, acc != 0u);
+                eval_fields<true, false>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
+                __syncwarp();
+                // count legal actions: lane sums popcounts over its contiguous chunk of fields (field order = id order);
+                // "has a move" falls out of the count, so the fields are not OR-reduced separately
+                if (kN == 20) {                 // 1665 fields = 32 x 52 (+1 for lane 31): 13 conflict-free LDS.128 per lane
+                    const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 13 * lane;
+#pragma unroll
+                    for (int j = 0; j < 13; ++j) {
+                        const uint4 x = f4[j];
+                        mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+                    }
+                    if (lane == 31) mine += __popc(fld[1664]);
+                } else {
+                    for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
+                }
+                incl = warp_incl_scan(mine, lane);
+                has = __shfl_sync(kAllLanes, incl, 31) > 0;
                 // a player without a move never gets one back (others only take cells away, and it places nothing
                 // itself), so it is not evaluated again for the rest of the playout
                 if (!has) stuck |= 1u << cand;
@@ -752,23 +768,8 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(co
                 over = true;
                 break;
             }
-            __syncwarp();
             e.meta = (e.meta & ~15u) | static_cast<uint32_t>(cand);
             if (cand == a.stop_player) break;              // caller's turn: hand the state back
-            // count legal actions: lane sums popcounts over its contiguous chunk of fields (field order = id order)
-            int mine = 0;
-            if (kN == 20) {                     // 1665 fields = 32 x 52 (+1 for lane 31): 13 conflict-free LDS.128 per lane
-                const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 13 * lane;
-#pragma unroll
-                for (int j = 0; j < 13; ++j) {
-                    const uint4 x = f4[j];
-                    mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
-                }
-                if (lane == 31) mine += __popc(fld[1664]);
-            } else {
-                for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
-            }
-            const int incl = warp_incl_scan(mine, lane);
             const int cnt = __shfl_sync(kAllLanes, incl, 31);
             const uint32_t ply = e.meta >> 16;
             if (static_cast<int>(ply >> 2) != rnd_block) {
