@@ -21,10 +21,15 @@ from pathlib import Path
 
 
 def sass_lines(so: Path, kernel: str):
-    tmp = Path(tempfile.mkdtemp())
-    subprocess.check_call(["cuobjdump", "-xelf", "all", str(so.resolve())], cwd=tmp, stdout=subprocess.DEVNULL)
-    txt = "\n".join(subprocess.run(["nvdisasm", "--print-line-info", str(c)], capture_output=True, text=True).stdout
-                    for c in sorted(tmp.glob("*.cubin")))     # one cubin per kernel specialisation object
+    # every kernel specialisation is its own object (same cubin name inside the .so): disassemble the objects
+    objs = sorted((so.resolve().parent / "build").glob("*.o")) or [so.resolve()]
+    chunks = []
+    for obj in objs:
+        tmp = Path(tempfile.mkdtemp())
+        subprocess.run(["cuobjdump", "-xelf", "all", str(obj)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for c in sorted(tmp.glob("*.cubin")):
+            chunks.append(subprocess.run(["nvdisasm", "--print-line-info", str(c)], capture_output=True, text=True).stdout)
+    txt = "\n".join(chunks)
     out, cur_line, active = [], ("?", 0), False
     for ln in txt.splitlines():
         if ln.startswith(".text."):
