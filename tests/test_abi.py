@@ -79,3 +79,16 @@ def test_missing_library_fails_loudly(tmp_path):
     env = dict(os.environ, BLOKUS_B200_LIB=str(tmp_path / "nope.so"))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert "LOUD True" in out.stdout, out.stdout + out.stderr
+
+
+def test_header_is_valid_c99_and_a_plain_c_program_links(lib, tmp_path):
+    """The ABI is C, not C++: examples/c_abi_smoke.c compiles with gcc -std=c99 and links against the .so
+    (it is run on the GPU box by tests/test_gpu_parity.py::test_plain_c_program_runs)."""
+    import subprocess
+    exe = tmp_path / "c_abi_smoke"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include",
+           str(ROOT / "examples" / "c_abi_smoke.c"), "-o", str(exe), "-L", str(ROOT / "blokus_rl_b200"),
+           "-lblokus_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{ROOT / 'blokus_rl_b200'}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert exe.exists()

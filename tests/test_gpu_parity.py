@@ -211,3 +211,17 @@ def test_full_size_properties_65536(engine20):
     scores = w[:, 86:88].copy().view(np.int16).reshape(n, 4)
     assert (scores == occupied).all()
     assert (rows[:, 0] & rows[:, 1]).sum() == 0 and (rows[:, 2] & rows[:, 3]).sum() == 0
+
+
+def test_plain_c_program_runs(tmp_path):
+    """examples/c_abi_smoke.c: the C ABI driven from plain C with cudaMalloc'd buffers (no torch, no Python)."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    exe = tmp_path / "c_abi_smoke"
+    cmd = ["gcc", "-std=c99", "-I", str(root / "include"), "-I", "/usr/local/cuda/include",
+           str(root / "examples" / "c_abi_smoke.c"), "-o", str(exe), "-L", str(root / "blokus_rl_b200"),
+           "-lblokus_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{root / 'blokus_rl_b200'}"]
+    subprocess.check_call(cmd)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "c_abi_smoke ok" in out.stdout, out.stdout + out.stderr
