@@ -65,7 +65,8 @@ class BlkPuctForest(C.Structure):
 
 class BlkPuctExpandArgs(C.Structure):
     _fields_ = [("new_slot_base", C.c_int32), ("state_words", C.c_int32), ("meta_word", C.c_int32),
-                ("attach_only", C.c_int32), ("new_states", C.c_void_p), ("mask", C.c_void_p), ("flags", C.c_void_p),
+                ("attach_only", C.c_int32), ("new_states", C.c_void_p), ("pool", C.c_void_p), ("mask", C.c_void_p),
+                ("flags", C.c_void_p),
                 ("terminal", C.c_void_p), ("prior", C.c_void_p), ("prior_dtype", C.c_int32), ("prior_stride", C.c_int64),
                 ("value", C.c_void_p)]
 

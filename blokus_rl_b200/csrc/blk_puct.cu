@@ -84,6 +84,7 @@ struct ExpandArgs {
     blk_puct_forest f;
     int32_t new_slot_base, state_words, meta_word, attach_only;
     const uint32_t *new_states;   // [B][state_words] states written by blk_step for this simulation
+    uint32_t *pool;               // state pool the new states are filed into (slot base + t), or NULL
     const uint8_t *mask;          // [B][mask_stride] byte masks of those states
     const uint8_t *flags;         // [B]
     const float *terminal;        // [B][P]
@@ -107,6 +108,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
         return;
     }
     int target = f.leaf_node[t];
+    // pool slot of this tree's new state: explicit base, or the device-side counter (CUDA-graph friendly)
+    const int slot = (a.new_slot_base >= 0 ? a.new_slot_base : f.counters[4]) + t;
+    if (slot >= f.node_capacity) { if (lane == 0) f.counters[2] = 1; if (lane < P) score[lane] = 0.0; return; }
+    if (a.pool != nullptr)
+        for (int i = lane; i < a.state_words; i += 32)
+            a.pool[static_cast<int64_t>(slot) * a.state_words + i] = a.new_states[static_cast<int64_t>(t) * a.state_words + i];
     if (st == BLK_PUCT_NEED_STEP) {
         const uint8_t fl = a.flags[t];
         int node = 0;
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
         if (node >= f.node_capacity) { if (lane == 0) f.counters[2] = 1; if (lane < P) score[lane] = 0.0; return; }
         const bool done = fl & BLK_FLAG_DONE;
         if (lane == 0) {
-            f.node_state[node] = a.new_slot_base + t;
+            f.node_state[node] = slot;
             f.node_mover[node] = static_cast<int8_t>(a.new_states[static_cast<int64_t>(t) * a.state_words + a.meta_word] & 15u);
             f.node_edge0[node] = -1;
             f.node_nedge[node] = 0;
@@ -201,6 +208,7 @@ __global__ void puct_backup_kernel(blk_puct_forest f) {
         f.edge_q[e] = __ddiv_rn(__dadd_rn(__dmul_rn(n, q), val), __dadd_rn(n, 1.0));
         f.edge_n[e] = __dadd_rn(n, 1.0);
     }
+    if (t == 0) f.counters[4] += f.num_trees;      // this simulation's B pool slots are taken (expand has finished)
 }
 
 // root <- child of the root edge carrying `action`; children that do not exist yet are requested as NEED_STEP
@@ -283,7 +291,7 @@ int blk_puct_expand(const blk_puct_forest *f, const blk_puct_expand_args *x, voi
     if (f->mask_stride % 8 != 0) return puct_fail("mask_stride must be a multiple of 8");
     ExpandArgs a;
     a.f = *f; a.new_slot_base = x->new_slot_base; a.state_words = x->state_words; a.meta_word = x->meta_word;
-    a.attach_only = x->attach_only; a.new_states = x->new_states; a.mask = x->mask; a.flags = x->flags;
+    a.attach_only = x->attach_only; a.new_states = x->new_states; a.pool = x->pool; a.mask = x->mask; a.flags = x->flags;
     a.terminal = x->terminal; a.prior = x->prior; a.prior_dtype = x->prior_dtype; a.prior_stride = x->prior_stride;
     a.value = x->value;
     const int grid = (f->num_trees + kWarpsPerBlock - 1) / kWarpsPerBlock;

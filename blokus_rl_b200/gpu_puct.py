@@ -22,7 +22,7 @@ from .mcts import UniformEvaluator
 
 class GpuPuct:
     def __init__(self, engine, evaluator=None, num_trees: int = 256, max_simulations: int = 4096,
-                 mean_edges_per_node: int = 256, max_depth: int = 96):
+                 mean_edges_per_node: int = 256, max_depth: int = 96, use_cuda_graph: bool = True):
         self.eng = engine
         self.evaluator = evaluator or UniformEvaluator()
         self.B, self.P, self.A = num_trees, engine.num_players, engine.num_actions
@@ -46,7 +46,7 @@ class GpuPuct:
             "path_len": torch.zeros(self.B, **i32), "status": torch.zeros(self.B, **i32),
             "leaf_node": torch.zeros(self.B, **i32), "leaf_edge": torch.zeros(self.B, **i32),
             "src_slot": torch.zeros(self.B, **i32), "step_action": torch.zeros(self.B, **i32),
-            "scores": torch.zeros((self.B, self.P), **f64), "counters": torch.zeros(4, **i32),
+            "scores": torch.zeros((self.B, self.P), **f64), "counters": torch.zeros(5, **i32),
         }
         self.pool = torch.empty((self.node_cap, engine.state_words), dtype=torch.int32, device=dev)
         self.used = 0
@@ -57,6 +57,10 @@ class GpuPuct:
                                              "root", "path", "path_len", "status", "leaf_node", "leaf_edge", "src_slot",
                                              "step_action", "scores", "counters")])
         self.buf = engine.make_buffers(self.B, "bytes")
+        self.stage = torch.empty((self.B, engine.state_words), dtype=torch.int32, device=dev)   # blk_step output
+        self.use_cuda_graph = use_cuda_graph and getattr(self.evaluator, "graph_safe", False)
+        self._graphs: dict = {}         # (cpuct, epsilon_fix) -> captured simulation
+        self._eager_runs = 0
         self.launches = 0
         self._meta = self.P * engine.board_size + self.P
 
@@ -83,45 +87,69 @@ class GpuPuct:
         t["node_mover"][:B] = (states[:, self._meta] & 15).to(torch.int8)
         t["node_terminal"][:B] = (flags & 1).to(torch.int8)
         t["node_term_value"][:B] = term.to(torch.float64)
-        t["counters"].copy_(torch.tensor([B, 0, 0, 0], dtype=torch.int32))
+        t["counters"].copy_(torch.tensor([B, 0, 0, 0, B], dtype=torch.int32))
 
     # ---- one simulation of every tree ---------------------------------------------------------------------------
     def _step_and_expand(self, attach_only: bool):
+        """blk_step on the requested transitions -> evaluator -> blk_puct_expand.  Every pointer and scalar passed
+        to a kernel here is the same on every call (new states go through `stage`, their pool slots come from a
+        device-side counter), so the sequence can be captured into a CUDA graph."""
         t, B, eng = self.t, self.B, self.eng
-        if self.used + B > self.node_cap:
-            raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
         src = self.pool.index_select(0, t["src_slot"].long())
-        dst = self.pool[self.used: self.used + B]
-        out = eng.step(src, t["step_action"], out_states=dst, buffers=self.buf, mask="bytes", want_count=False,
+        out = eng.step(src, t["step_action"], out_states=self.stage, buffers=self.buf, mask="bytes", want_count=False,
                        want_scores=False)
         prior, pd, ps, value = None, 0, 0, None
         if not attach_only and not isinstance(self.evaluator, UniformEvaluator):
-            p, v = self.evaluator.evaluate(eng, dst, out.mask)
+            p, v = self.evaluator.evaluate(eng, self.stage, out.mask)
             prior = p.contiguous()
             pd = 2 if prior.dtype == torch.float64 else 1
             if pd == 1:
                 prior = prior.float()
             ps = prior.stride(0)
             value = v.to(torch.float64).contiguous()
-        args = _lib.BlkPuctExpandArgs(self.used, eng.state_words, self._meta, int(attach_only), dst.data_ptr(),
-                                      out.mask_raw.data_ptr(), out.flags.data_ptr(), out.terminal.data_ptr(),
-                                      None if prior is None else prior.data_ptr(), pd, ps,
+        args = _lib.BlkPuctExpandArgs(-1, eng.state_words, self._meta, int(attach_only), self.stage.data_ptr(),
+                                      self.pool.data_ptr(), out.mask_raw.data_ptr(), out.flags.data_ptr(),
+                                      out.terminal.data_ptr(), None if prior is None else prior.data_ptr(), pd, ps,
                                       None if value is None else value.data_ptr())
         self._check(self._lib.blk_puct_expand(C.byref(self.forest), C.byref(args), self._stream()))
-        self.used += B
-        self.launches += 3 if prior is None else 4
+        self._keep = (src, prior, value)                 # keep graph-captured temporaries alive
 
-    def simulate(self, cpuct: float = 1.0, epsilon_fix: bool = True) -> None:
+    def _simulate_eager(self, cpuct: float, epsilon_fix: bool) -> None:
         self._check(self._lib.blk_puct_select(C.byref(self.forest), float(cpuct), int(epsilon_fix), self._stream()))
         self._step_and_expand(False)
         self._check(self._lib.blk_puct_backup(C.byref(self.forest), self._stream()))
-        self.launches += 2
+
+    def simulate(self, cpuct: float = 1.0, epsilon_fix: bool = True) -> None:
+        """One simulation of every tree.  After two eager runs the launch sequence is captured into a CUDA graph
+        (one per (cpuct, epsilon_fix)) and replayed: small batches stop being launch-bound."""
+        if self.used + self.B > self.node_cap:
+            raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
+        key = (float(cpuct), bool(epsilon_fix))
+        g = self._graphs.get(key)
+        if g is not None:
+            g.replay()
+        elif self.use_cuda_graph and self._eager_runs >= 2:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.eng.device)
+            with torch.cuda.graph(g):
+                self._simulate_eager(cpuct, epsilon_fix)
+            self._graphs[key] = g
+            g.replay()                                   # capture only records: run the simulation it stands for
+        else:
+            self._simulate_eager(cpuct, epsilon_fix)
+            self._eager_runs += 1
+        self.used += self.B
+        self.launches += 5
 
     def advance(self, actions: torch.Tensor) -> None:
         """Make the child under ``actions[t]`` the root of tree t (``-1`` leaves a tree where it is)."""
         acts = actions.to(torch.int32).contiguous()
+        if self.used + self.B > self.node_cap:
+            raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
         self._check(self._lib.blk_puct_advance(C.byref(self.forest), acts.data_ptr(), self._stream()))
         self._step_and_expand(True)
+        self._check(self._lib.blk_puct_backup(C.byref(self.forest), self._stream()))   # empty paths: only takes the pool slots
+        self.used += self.B
 
     # ---- results (host side; synchronises) ---------------------------------------------------------------------------
     def check(self) -> None:

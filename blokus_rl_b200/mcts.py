@@ -30,6 +30,8 @@ import torch
 # evaluators:  evaluate(engine, states int32 [m, SW], mask bool [m, A]) -> (p [m, A] float, v [m, P] float)
 # ------------------------------------------------------------------------------------------------
 class UniformEvaluator:
+    graph_safe = True          # no host work: GpuPuct may capture it into a CUDA graph
+
     def evaluate(self, engine, states, mask):
         cnt = mask.sum(1, keepdim=True).clamp(min=1).to(torch.float64)
         return mask.to(torch.float64) / cnt, torch.zeros((states.shape[0], engine.num_players), dtype=torch.float64,
@@ -50,6 +52,8 @@ class RolloutEvaluator:
 
 
 class TorchNetEvaluator:
+    graph_safe = True          # static-shape torch ops only
+
     def __init__(self, model: torch.nn.Module):
         self.model = model
 

@@ -173,14 +173,16 @@ typedef struct {
     int32_t *src_slot;            /* [B] state slot blk_step must read for this tree */
     int32_t *step_action;         /* [B] action for blk_step (BLK_ACTION_NONE: evaluate the state as it is) */
     double *scores;               /* [B][P] score vector of the current simulation */
-    int32_t *counters;            /* [4] nodes used, edges used, capacity overflow flag, illegal-action flag */
+    int32_t *counters;            /* [5] nodes used, edges used, capacity overflow flag, illegal-action flag, pool slots used */
 } blk_puct_forest;
 
 typedef struct {
-    int32_t new_slot_base;        /* pool slot of tree 0's new state; tree t uses new_slot_base + t */
+    int32_t new_slot_base;        /* pool slot of tree 0's new state (tree t uses base + t); -1: take counters[4], which
+                                     blk_puct_backup advances by B (keeps every argument constant: CUDA-graph capture) */
     int32_t state_words, meta_word;   /* engine state_words and the index of the meta word (P*N + P) */
     int32_t attach_only;          /* 1: only create the requested child nodes and make them the roots (blk_puct_advance) */
     const uint32_t *new_states;   /* [B][state_words] */
+    uint32_t *pool;               /* nullable: state pool; the new states are copied to slots base + t */
     const uint8_t *mask;          /* [B][mask_stride] */
     const uint8_t *flags;         /* [B] */
     const float *terminal;        /* [B][P] */

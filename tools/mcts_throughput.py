@@ -33,9 +33,10 @@ for B, sims, ev, name in ((256, 50, UniformEvaluator(), "uniform"), (4096, 50, U
     out = eng.step(s, None, mask=None, sample=True, seed=1)
     for _ in range(16):
         out = eng.step(s, out.next_action, mask=None, sample=True, seed=1)
-    search = GpuPuct(eng, ev, num_trees=B, max_simulations=sims + 4, mean_edges_per_node=420)
+    search = GpuPuct(eng, ev, num_trees=B, max_simulations=sims + 8, mean_edges_per_node=420)
     search.set_roots(s)
-    search.simulate()
+    for _ in range(4):                 # two eager runs, the CUDA-graph capture, one replay
+        search.simulate()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(sims):
