@@ -113,7 +113,10 @@ def test_functional_step_keeps_input(engine20):
 
 def test_observation_and_board_contents(engine20, oracle20, engine7, oracle7):
     import torch
-    for eng, orc in ((engine20, oracle20), (engine7, oracle7)):
+    from blokus_rl_b200 import BlokusEngine
+    from oracle.oracle import Oracle
+    extra = [(BlokusEngine(n, p), Oracle(n, p)) for n, p in ((20, 2), (14, 2), (14, 4))]   # other streaming-kernel variants
+    for eng, orc in [(engine20, oracle20), (engine7, oracle7)] + extra:
         sts = []
         for g in range(6):
             o = orc.new_state()
