@@ -217,7 +217,7 @@ struct blk_engine {
     unsigned long long *d_queue = nullptr;   // kQueueSlots x {ticket, finished}; launch i uses slot i % kQueueSlots
     unsigned launch_seq = 0;
     int sm_count = 0;
-    int step_smem = 0;
+    int step_smem = 0, roll_smem = 0;
     int step_blocks_per_sm = 0, rollout_blocks_per_sm = 0;
     bool special = false;
     KernelSet ks = {};                               // step[mask format variant][sampler], rollout
@@ -273,10 +273,11 @@ int build_tables(blk_engine *h) {
     g.rounds = (g.mw + 31) / 32;
     int off = kOffWdesc + 8 * 32 * g.rounds;               // LUT at 0, gather descriptors at 2048
     t.off_obase = off;  off = align16(off + 4 * (kOrients + 1));
+    t.off_wsrc = off;   off = align16(off + 2 * g.mw);
+    t.roll_begin = off;                                      // everything from here on is what the rollout kernel stages
     t.off_oinfo = off;  off = align16(off + 4 * (kOrients + 1));
     t.off_ocells = off; off = align16(off + 4 * (kOrients + 1));
     t.off_foff = off;   off = align16(off + 2 * (g.nf + 1));
-    t.off_wsrc = off;   off = align16(off + 2 * g.mw);
     t.off_fbase = off;  off = align16(off + 2 * (kOrients + 1));
     t.off_f2o = off;    off = align16(off + g.nf);
     t.bytes = off;
@@ -372,6 +373,7 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     int rc = build_tables(h);
     if (rc != BLK_OK) { blk_destroy(h); return rc; }
     h->step_smem = h->t.bytes + 16 + kWarps * h->g.warp_smem;
+    h->roll_smem = (h->t.bytes - h->t.roll_begin) + 16 + kRollWarps * h->g.warp_smem;
     // specialised kernels for the geometries the reference's configs name, runtime-dimension kernels otherwise
     const int N = cfg->board_size, P = cfg->num_players;
     int geom = 0;
@@ -386,7 +388,7 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     static int s_max_smem[16][6] = {};
     int &cur_max = s_max_smem[cfg->device & 15][geom];
     if (h->step_smem > cur_max) {
-        cudaError_t err = cudaFuncSetAttribute(h->ks.rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+        cudaError_t err = cudaFuncSetAttribute(h->ks.rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem);
         for (int f = 0; f < 4 && err == cudaSuccess; ++f)
             for (int sm = 0; sm < 2 && err == cudaSuccess; ++sm)
                 err = cudaFuncSetAttribute(h->ks.step[f][sm], cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
@@ -394,7 +396,7 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
         cur_max = h->step_smem;
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_blocks_per_sm, h->ks.step[2][1], kWarps * 32, h->step_smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, h->ks.rollout, kWarps * 32, h->step_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, h->ks.rollout, kRollWarps * 32, h->roll_smem);
     if (h->step_blocks_per_sm < 1 || h->rollout_blocks_per_sm < 1) { blk_destroy(h); return fail(BLK_ERR_CUDA, "kernel does not fit on an SM"); }
     *out = h;
     return BLK_OK;
@@ -525,8 +527,8 @@ int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream) {
     RParams rp;
     rp.a = *args; rp.tables = h->d_tables; rp.t = h->t; rp.g = h->g;
     rp.queue = h->d_queue + 2 * (h->launch_seq++ % kQueueSlots);
-    const int grid = grid_for(args->n_roots * args->per_root, kWarps, h->sm_count, h->rollout_blocks_per_sm);
-    h->ks.rollout<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(rp);
+    const int grid = grid_for(args->n_roots * args->per_root, kRollWarps, h->sm_count, h->rollout_blocks_per_sm);
+    h->ks.rollout<<<grid, kRollWarps * 32, h->roll_smem, static_cast<cudaStream_t>(stream)>>>(rp);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
 }

@@ -29,7 +29,12 @@ constexpr int kSumH = 246;  // sum of bounding-box heights over the 91 orientati
 #define BLK_WARPS 8
 #define BLK_MIN_BLOCKS 3
 #endif
-constexpr int kWarps = BLK_WARPS;   // warps (= envs in flight) per block
+constexpr int kWarps = BLK_WARPS;   // warps (= envs in flight) per block of the step kernel
+#ifndef BLK_ROLL_WARPS
+#define BLK_ROLL_WARPS 7
+#define BLK_ROLL_MIN_BLOCKS 4
+#endif
+constexpr int kRollWarps = BLK_ROLL_WARPS;   // playouts in flight per block of the rollout kernel (slim tables: 4 blocks/SM)
 constexpr uint32_t kFullInv = (1u << kPieces) - 1u;
 constexpr uint32_t kAllLanes = 0xffffffffu;
 #ifndef BLK_ST_POLICY
@@ -64,6 +69,7 @@ struct TableLayout {
     int off_fbase;   // uint16[92]  first field index of each orientation
     int off_f2o;     // uint8[nf]   orientation of each field
     int bytes;       // multiple of 16
+    int roll_begin;  // the rollout kernel stages only [roll_begin, bytes): oinfo, ocells, foff, fbase, f2o
     // Two tables sit at FIXED offsets so their shared-memory addresses are immediates in the unrolled emit loop:
     //   kOffLut   = 0     uint2[256]        byte -> 8 bytes of 0/1 (bit i -> byte i)
     //   kOffWdesc = 2048  uint2[32*rounds]  gather descriptor of mask word g (valid when <= 3 fields meet a word):
@@ -409,7 +415,8 @@ struct SmemTables {
     const uint2 *wdesc;
     const uint2 *lut;
 };
-__device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, const TableLayout &t) {
+__device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, const TableLayout &t, int shift = 0) {
+    tab -= shift;                                   // `tab` holds the blob from byte `shift` on
     SmemTables tb;
     tb.obase = reinterpret_cast<const int32_t *>(tab + t.off_obase);
     tb.oinfo = reinterpret_cast<const uint32_t *>(tab + t.off_oinfo);
@@ -699,16 +706,17 @@ struct RParams {
 };
 
 template <int kN, int kP>
-__global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) rollout_kernel(const RParams rp) {
+__global__ void __launch_bounds__(kRollWarps * 32, BLK_ROLL_MIN_BLOCKS) rollout_kernel(const RParams rp) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Geometry &gg = rp.g;
     const Dims g = make_dims<kN, kP>(gg);
     const blk_rollout_args &a = rp.a;
     unsigned char *tab = smem;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + rp.t.bytes);
-    unsigned char *scratch = smem + rp.t.bytes + 16;
-    tma_load_tables(tab, rp.tables, rp.t.bytes, bar);
-    const SmemTables tb = make_tables(tab, rp.t);
+    const int tab_bytes = rp.t.bytes - rp.t.roll_begin;          // only the tables a playout needs (~6 KB of ~19 KB)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + tab_bytes);
+    unsigned char *scratch = smem + tab_bytes + 16;
+    tma_load_tables(tab, rp.tables + rp.t.roll_begin, tab_bytes, bar);
+    const SmemTables tb = make_tables(tab, rp.t, rp.t.roll_begin);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * gg.warp_smem);
