@@ -614,6 +614,9 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
         if (kFmt != 0 || kSample || want_count) {
             unsigned char *row = reinterpret_cast<unsigned char *>(a.mask) + env * mstride + 16 * lane;
             uint32_t *wrow = reinterpret_cast<uint32_t *>(a.mask) + env * mstride + lane;
+            unsigned char *urow = reinterpret_cast<unsigned char *>(a.mask) + env * mstride;     // kFmt == 3 only
+            const int ush = static_cast<int>(reinterpret_cast<uintptr_t>(urow) & 15);
+            uint32_t uprev = 0u;
 #pragma unroll(kEmitUnroll)
             for (int r = 0; r < (kN == 20 ? 30 : rounds); ++r) {
                 uint32_t word;
@@ -641,12 +644,33 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                         if (r < (kN == 20 ? 29 : rounds - 1) || boff + 16 * lane < mask_bytes)
                             BLK_STORE16(reinterpret_cast<uint4 *>(row + boff), make_uint4(lo.x, lo.y, hi.x, hi.y));
                     }
-                } else if (kFmt == 3) {  // unaligned caller buffer: correct but slow byte stores
-                    unsigned char *urow = reinterpret_cast<unsigned char *>(a.mask) + env * mstride;
-                    for (int b = 0; b < 32; ++b) {
-                        const int idx = (((r << 5) + lane) << 5) + b;
-                        if (idx < g.A) urow[idx] = static_cast<unsigned char>((word >> b) & 1u);
+                } else if (kFmt == 3) {
+                    // Caller buffer with any base / row stride (e.g. a contiguous bool [n, A]): the row starts `ush`
+                    // bytes into a 16 B chunk.  Still one 16 B store per lane on chunk-aligned addresses: chunk c of
+                    // this pass holds row bytes [1024 r + 16 c - ush, +16), i.e. 16 mask bits that straddle at most two
+                    // words (the word before this pass comes from `uprev`).  Only the chunks that overlap the row ends
+                    // fall back to byte stores, so neighbouring rows (other warps) are never touched.
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = 32 * h + lane;
+                        const int rb = 16 * c - ush;                          // bit offset inside this pass, >= -15
+                        const int wi = rb >> 5;                               // -1 .. 31
+                        const uint32_t lo_w = __shfl_sync(kAllLanes, word, wi & 31);
+                        const uint32_t hi_w = __shfl_sync(kAllLanes, word, (wi + 1) & 31);
+                        const uint32_t bits = __funnelshift_r(wi < 0 ? uprev : lo_w, hi_w, rb & 31) & 0xffffu;
+                        const uint2 lo = *reinterpret_cast<const uint2 *>(lutb + ((bits << 3) & 0x7f8u));
+                        const uint2 hi = *reinterpret_cast<const uint2 *>(lutb + ((bits >> 5) & 0x7f8u));
+                        const int p0 = (r << 10) + rb;                        // row position of the chunk's first byte
+                        unsigned char *dst = urow + p0;                       // 16 B aligned by construction
+                        if (p0 >= 0 && p0 + 16 <= g.A) {
+                            BLK_STORE16(reinterpret_cast<uint4 *>(dst), make_uint4(lo.x, lo.y, hi.x, hi.y));
+                        } else if (p0 + 16 > 0 && p0 < g.A) {                 // first / last chunk of the row
+                            const uint32_t v[4] = {lo.x, lo.y, hi.x, hi.y};
+                            for (int b = 0; b < 16; ++b)
+                                if (p0 + b >= 0 && p0 + b < g.A) dst[b] = static_cast<unsigned char>((v[b >> 2] >> (8 * (b & 3))) & 1u);
+                        }
                     }
+                    uprev = __shfl_sync(kAllLanes, word, 31);
                 }
             }
             if (!kSample) cnt = warp_sum(cnt);

@@ -156,6 +156,8 @@ class BlokusEngine:
                 raise ValueError("mask buffer must be uint8/bool (bytes) or int32 (bits)")
             if raw_mask.shape[0] != n or raw_mask.stride(1) != 1:
                 raise ValueError("mask buffer must have n rows with unit column stride")
+            if fmt == BLK_MASK_BYTES and raw_mask.shape[1] < self.num_actions:
+                raise ValueError("byte-mask rows must hold num_actions bytes")
 
         def buf(name, shape, dtype, want):
             if not want:

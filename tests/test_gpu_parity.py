@@ -138,15 +138,28 @@ def test_observation_and_board_contents(engine20, oracle20, engine7, oracle7):
             assert (term[i].cpu().numpy() == orc.terminal_values(o)).all()
 
 
-def test_unaligned_and_contiguous_bool_mask(engine20, oracle20):
-    """A caller-provided contiguous bool [n, 30433] buffer (row stride not a multiple of 16) still works."""
+def test_unaligned_and_contiguous_bool_mask(engine20, oracle20, engine7):
+    """Caller-provided contiguous bool [n, A] buffers (row stride 30,433: every row starts at a different offset inside
+    a 16 B chunk) and arbitrarily offset bases give the same masks as the padded layout, and neighbours stay intact."""
     import torch
-    s = engine20.new_states(3)
-    raw = torch.zeros((3, engine20.num_actions), dtype=torch.uint8, device=s.device)
-    out = engine20.step(s, None, mask=raw)
-    torch.cuda.synchronize()
-    assert (raw[0].cpu().numpy() == oracle20.legal_mask(oracle20.new_state())).all()
-    assert out.mask.shape == (3, engine20.num_actions)
+    for eng in (engine20, engine7):
+        n, A = 70, eng.num_actions
+        s = eng.new_states(n)
+        out = eng.step(s, None, mask="bytes", sample=True, seed=9)
+        for _ in range(14 if eng.board_size == 20 else 3):
+            out = eng.step(s, out.next_action, mask="bytes", sample=True, seed=9)
+        want = out.mask.clone()
+        assert (want.sum(1) > 0).all()
+        for base_off, stride in ((0, A), (1, A), (7, A + 3), (13, A + 16), (16, A)):
+            raw = torch.full((base_off + n * stride + 64,), 7, dtype=torch.uint8, device=s.device)
+            view = raw[base_off: base_off + n * stride].view(n, stride)[:, :A]
+            got = eng.step(s, None, mask=view)
+            torch.cuda.synchronize()
+            assert got.mask.shape == (n, A)
+            assert (view.bool() == want).all(), (base_off, stride)
+            assert (raw[:base_off] == 7).all() and (raw[base_off + n * stride:] == 7).all()      # nothing outside the rows
+            if stride > A:
+                assert (raw[base_off: base_off + n * stride].view(n, stride)[:, A:] == 7).all()   # nor between them
 
 
 def test_rollouts_replay_through_oracle(engine20, oracle20):
