@@ -23,3 +23,38 @@ for (N, P, rule, n, plies, seed) in ((20, 4, 0, 1500, 200, 11), (20, 4, 1, 600, 
     total_steps += steps; total_games += games
     eng.close()
 print(f"SOAK OK: {total_steps} env steps, {total_games} games, {time.time() - t0:.0f} s")
+
+# ---- playouts: every logged action replayed through the oracle (same Philox stream), final scores and winners compared ----
+import numpy as np
+import torch
+for (N, P, rule, n_roots, per_root, root_plies) in ((20, 4, 0, 48, 32, 24), (20, 4, 1, 24, 16, 40), (14, 2, 0, 48, 32, 10), (7, 2, 0, 64, 32, 2)):
+    eng, orc = BlokusEngine(N, P, score_rule=rule), Oracle(N, P, rule)
+    roots = []
+    for g in range(n_roots):
+        o = orc.new_state()
+        for _ in range(root_plies):
+            if orc.field(o, "done"):
+                break
+            orc.step(o, orc.sample_action(o, 5, g), fast=True)
+        roots.append(o)
+    words = torch.tensor(np.stack([orc.pack(o) for o in roots]).view(np.int32)).cuda()
+    seed = 0xC0FFEE + N
+    out = eng.rollout(words, per_root, seed=seed, log_actions=True)
+    torch.cuda.synchronize()
+    log = out.action_log.cpu().numpy().view(np.uint16)
+    fs, win, plies = out.final_scores.cpu().numpy(), out.winners.cpu().numpy(), out.plies.cpu().numpy()
+    nply = 0
+    for r, root in enumerate(roots):
+        for j in range(per_root):
+            o = orc.copy(root)
+            k = 0
+            while not orc.field(o, "done"):
+                a = int(log[r, j, k])
+                assert a == orc.sample_action(o, seed, r * per_root + j, stream=1)
+                assert orc.step(o, a, fast=True) == 0
+                k += 1
+            assert plies[r, j] == k and (fs[r, j] == orc.final_scores(o)[:P]).all() and win[r, j] == orc.winners(o)
+            nply += k
+    print(f"playouts {N}x{N} {P}p rule {rule}: {n_roots * per_root} playouts, {nply} plies replayed through the oracle -- identical", flush=True)
+    eng.close()
+print("SOAK PLAYOUTS OK")
