@@ -107,15 +107,18 @@ class ClockSampler:
             self.err = repr(e)
             self.h = None
 
-    def _poll(self):
+    def sample_now(self):
         nv = self.nv
+        try:
+            self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            pass
+
+    def _poll(self):
         while not self._stop.is_set():
-            try:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-            except Exception:
-                pass
-            time.sleep(0.01)
+            self.sample_now()
+            time.sleep(0.005)
 
     def stop(self):
         if self.h is None:
@@ -172,6 +175,8 @@ def run_ours(args):
     for k in range(args.steps):
         out = step()
         evs[k + 1].record()
+    if sampler is not None and sampler.h is not None:
+        sampler.sample_now()                    # the queue is still draining: at least one sample under load, however short the run
     sync_all()
     total_ms = evs[0].elapsed_time(evs[-1])
     per_launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
