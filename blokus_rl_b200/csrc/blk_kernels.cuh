@@ -206,6 +206,14 @@ __device__ __forceinline__ Dims make_dims(const Geometry &g) {
 // Dynamic work distribution: warps draw env indices from a global ticket counter instead of a fixed stride, so
 // nobody idles in the last wave (65,536 envs over 3,552 resident warps is 18.45 each) and uneven envs
 // (skipped players, finished games) even out.  The last block to finish resets the counters for the next launch.
+// split form: issue the atomic early (lane 0 keeps the result), broadcast it only where the index is needed, so the
+// ~1 us round trip to L2 overlaps a whole env instead of stalling the warp
+__device__ __forceinline__ unsigned long long ticket_issue(unsigned long long *queue, int lane) {
+    return lane == 0 ? atomicAdd(queue, 1ULL) : 0ULL;
+}
+__device__ __forceinline__ int64_t ticket_get(unsigned long long t) {
+    return static_cast<int64_t>(__shfl_sync(kAllLanes, t, 0));
+}
 __device__ __forceinline__ int64_t next_ticket(unsigned long long *queue, int lane) {
     unsigned long long t = 0;
     if (lane == 0) t = atomicAdd(queue, 1ULL);
@@ -534,14 +542,15 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
     // software pipeline over this warp's envs: the next env's 352 B and action are fetched while the current one
     // is processed (a warp handles its envs serially; without this every env starts with an exposed HBM round trip)
     int64_t env = next_ticket(kp.queue, lane);
-    int64_t env_next = next_ticket(kp.queue, lane), env_after = 0;
+    int64_t env_next = next_ticket(kp.queue, lane);
+    unsigned long long pending = 0ULL;
     EnvRaw raw_next = {};
     int act_next = BLK_ACTION_NONE;
     if (env < n) {
         raw_next = env_fetch(a.state_in + env * sw, g, lane);
         if (a.action != nullptr) act_next = __ldg(a.action + env);
     }
-    for (; env < n; env = env_next, env_next = env_after) {
+    for (; env < n; env = env_next, env_next = ticket_get(pending)) {
         EnvRegs e;
         env_unpack(e, raw_next, g);
         const int act = act_next;
@@ -549,7 +558,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
             raw_next = env_fetch(a.state_in + env_next * sw, g, lane);
             if (a.action != nullptr) act_next = __ldg(a.action + env_next);
         }
-        env_after = next_ticket(kp.queue, lane);
+        pending = ticket_issue(kp.queue, lane);             // broadcast by the loop increment, one env later
         const bool was_done = (e.meta >> 4) & 1u;
         const int mover = e.meta & 15u;
         uint32_t flags = 0u;
