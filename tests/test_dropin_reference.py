@@ -100,3 +100,27 @@ def test_reference_mcts_player_over_shim(ref):
         s, cur = player.update_state(s, cur)
     assert ref.backend.ply(s[0]._h) == 3
     assert len(player.tree.tree) >= 6
+
+
+def test_reference_wrapper_over_shim_at_7x7_two_players(tmp_path):
+    """The PPO-config geometry (7x7, 2 players) through the reference's wrapper + a full arena game."""
+    import os
+    from blokus_rl_b200 import colosseum_shim, tables
+    backend = OracleBackend(7, 2)
+    colosseum_shim.set_backend(backend)
+    colosseum_shim.install()
+    ref_stubs.install_stubs()
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        from blokus_rl.colossumrl.blokus_wrapper import ColosseumBlokusGameWrapper
+        from blokus_rl.alphazero.arena import play_match
+        from blokus_rl.players import MCTSPlayer, RandomPlayer
+        game = ColosseumBlokusGameWrapper(types.SimpleNamespace(board_size=7, number_of_players=2, states_dir=tmp_path / "states"))
+        assert game.get_action_size() == 2522 and game._move_action_dict == tables.string_to_action(7)
+        np.random.seed(4)
+        scores, items = play_match(game, [MCTSPlayer(game, UniformNet(2), simulations=5), RandomPlayer(game)], games_num=2, permute=True)
+        assert len(items) == 2 and all(set(np.unique(it["scores"])) <= {-1.0, 1.0, 3.0} for it in items)
+    finally:
+        os.chdir(cwd)
+        colosseum_shim.set_backend(None)

@@ -150,3 +150,21 @@ def test_two_rank_gloo_run_equals_single_rank_run():
     (global env ids make the trajectories partition-invariant)."""
     one, two = _run_world(1), _run_world(2)
     assert one == two and one["steps"] == 120 and one["games"] > 0 and one["illegal"] == 0
+
+
+def test_vector_env_four_players_agent_not_first():
+    """4-player board, the agent sits in seat 2: three random bots move around it inside reset/step."""
+    from blokus_rl_b200.vector_env import BlokusVectorEnv
+    env = BlokusVectorEnv(5, engine=OracleEngine(7, 4), seed=1, agent_player=2)
+    obs, _ = env.reset()
+    assert obs.shape == (5, 7, 7) and (obs > 0).any()              # seats 0 and 1 have already moved
+    assert set(np.unique(obs)) <= {0.0, 1.0, 2.0}
+    rng = np.random.default_rng(3)
+    episodes = 0
+    for _ in range(25):
+        poss = env.get_attr("ai_possible_indexes")
+        acts = np.array([rng.choice(p) if p else -1 for p in poss])
+        obs, reward, terminated, truncated, info = env.step(acts)
+        episodes += int(terminated.sum())
+        assert (reward[~terminated] == 0).all()
+    assert episodes >= 5
