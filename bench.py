@@ -280,6 +280,12 @@ def run_ours(args):
         target = 12.0                                         # seconds of CPU work
         p1, s1 = cpu_random_play(2000 * cores, cores)
         plies, secs = cpu_random_play(int(p1 / s1 * target), cores)
+        from oracle.oracle import Oracle
+        o7 = Oracle(7, 2)
+        s7 = o7.new_state()
+        t7 = time.perf_counter()
+        n7, _, _ = o7.random_play(s7, 0, 0, 20000, auto_reset=True, fast=True, log=False)
+        line.setdefault("extra", {})["cpu_7x7_2p_single_env_plies_per_s"] = n7 / (time.perf_counter() - t7)   # BASELINE configs[0]
         line["cpu_baseline"] = {"value": plies / secs, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{plies} plies of 20x20 4p random-legal play with full byte masks, one env per "
                                           f"host thread, {secs:.1f} s (oracle port, bit-parallel variant)"}
