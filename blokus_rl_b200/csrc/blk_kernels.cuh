@@ -20,7 +20,7 @@
 
 namespace blk {
 
-
+// ---- compile-time knobs; the defaults are the measured optima on B200 ----
 constexpr int kMaxN = 20;
 constexpr int kPieces = 21;
 constexpr int kOrients = 91;
@@ -186,8 +186,8 @@ __device__ __forceinline__ int warp_sum(int v) {
     return v;
 }
 
-// Board dimensions as seen by the device helpers.  The kernels are instantiated for <N=20, P=4> (every member a
-// compile-time constant after inlining) and for <0, 0> (runtime values from Geometry).
+// Board dimensions as seen by the device helpers.  In the <N, P> specialisations (20x20, 14x14, 7x7) N, P and `full`
+// are compile-time constants after inlining; the <0, 0> kernels take them from Geometry at run time.
 struct Dims {
     int N, P, A, score_rule;
     uint32_t full;
@@ -206,8 +206,8 @@ __device__ __forceinline__ Dims make_dims(const Geometry &g) {
 // Dynamic work distribution: warps draw env indices from a global ticket counter instead of a fixed stride, so
 // nobody idles in the last wave (65,536 envs over 3,552 resident warps is 18.45 each) and uneven envs
 // (skipped players, finished games) even out.  The last block to finish resets the counters for the next launch.
-// split form: issue the atomic early (lane 0 keeps the result), broadcast it only where the index is needed, so the
-// ~1 us round trip to L2 overlaps a whole env instead of stalling the warp
+// ticket_issue / ticket_get split the fetch: the atomic is issued early (lane 0 keeps the result) and broadcast only
+// where the index is needed, so its round trip to L2 overlaps a whole env instead of stalling the warp.
 __device__ __forceinline__ unsigned long long ticket_issue(unsigned long long *queue, int lane) {
     return lane == 0 ? atomicAdd(queue, 1ULL) : 0ULL;
 }
@@ -424,7 +424,7 @@ struct SmemTables {
     const uint2 *lut;
 };
 __device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, const TableLayout &t, int shift = 0) {
-    tab -= shift;                                   // `tab` holds the blob from byte `shift` on
+    tab -= shift;   // `tab` holds the blob from byte `shift` on (rollout kernel): tables before it must not be touched
     SmemTables tb;
     tb.obase = reinterpret_cast<const int32_t *>(tab + t.off_obase);
     tb.oinfo = reinterpret_cast<const uint32_t *>(tab + t.off_oinfo);
