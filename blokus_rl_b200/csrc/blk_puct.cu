@@ -26,12 +26,6 @@ namespace {
 constexpr uint32_t kAll = 0xffffffffu;
 constexpr int kWarpsPerBlock = 4;
 
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kAll, v, d);   // exact: every term is an integer-valued double
-    return v;
-}
-
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_select_kernel(blk_puct_forest f, double cpuct, int eps_fix) {
     const int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -44,9 +38,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_select_kernel(blk_pu
         if (e0 < 0) { status = BLK_PUCT_NEED_EVAL; src = f.node_state[node]; break; }
         if (len == f.max_depth) { if (lane == 0) f.counters[2] = 1; status = BLK_PUCT_TERMINAL; break; }
         const int n = f.node_nedge[node];
-        double s = 0.0;
-        for (int i = lane; i < n; i += 32) s += f.edge_n[e0 + i];
-        s = warp_sum_d(s);
+        const double s = f.node_sum_n[node];           // sum of the edges' visit counts, maintained by the backup
         const double c = depth == 0 ? cpuct : 1.0;
         const double sq = __dsqrt_rn(__dadd_rn(s, (eps_fix || depth > 0) ? 1e-6 : 0.0));
         double best = -1.0e300;
@@ -63,7 +55,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_select_kernel(blk_pu
             if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
         }
         const int e = e0 + besti;
-        if (lane == 0) f.path[static_cast<int64_t>(t) * f.max_depth + len] = e;
+        if (lane == 0) {
+            f.path[static_cast<int64_t>(t) * f.max_depth + len] = e;
+            f.path_node[static_cast<int64_t>(t) * f.max_depth + len] = node;
+        }
         ++len;
         const int child = f.edge_child[e];
         if (child < 0) { status = BLK_PUCT_NEED_STEP; leaf_edge = e; src = f.node_state[node]; act = f.edge_action[e]; break; }
@@ -85,7 +80,9 @@ struct ExpandArgs {
     int32_t new_slot_base, state_words, meta_word, attach_only;
     const uint32_t *new_states;   // [B][state_words] states written by blk_step for this simulation
     uint32_t *pool;               // state pool the new states are filed into (slot base + t), or NULL
-    const uint8_t *mask;          // [B][mask_stride] byte masks of those states
+    const uint8_t *mask;          // [B][mask_stride] byte masks of those states, or bit-packed rows (mask_bits)
+    int32_t mask_bits;            // 1: `mask` holds bit-packed rows of mask_stride_words uint32 words
+    int32_t mask_stride_words;
     const uint8_t *flags;         // [B]
     const float *terminal;        // [B][P]
     const void *prior;            // [B][prior_stride] float32 / float64, or NULL for the uniform prior
@@ -129,6 +126,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
             f.node_mover[node] = static_cast<int8_t>(a.new_states[static_cast<int64_t>(t) * a.state_words + a.meta_word] & 15u);
             f.node_edge0[node] = -1;
             f.node_nedge[node] = 0;
+            f.node_sum_n[node] = 0.0;
             f.node_terminal[node] = done ? 1 : 0;
             f.edge_child[f.leaf_edge[t]] = node;
             if (a.attach_only) f.root[t] = node;
@@ -141,14 +139,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
         return;
     }
     // ---- expand `target`: one edge per legal action, ascending ids (np.where order, mcts.py:64) ----
-    const uint8_t *row = a.mask + static_cast<int64_t>(t) * f.mask_stride;
+    const int64_t mstride = a.mask_bits ? a.mask_stride_words : f.mask_stride;
+    const uint8_t *row = a.mask + static_cast<int64_t>(t) * mstride * (a.mask_bits ? 4 : 1);
     const int nwords = (f.num_actions + 31) >> 5;
     const int rounds = (nwords + 31) >> 5;                       // <= 32 words per lane
     uint32_t *words = s_words[warp];
     for (int r = 0; r < rounds; ++r) {
         const int g = (r << 5) + lane;
         uint32_t w = 0u;
-        if (g < nwords) {
+        if (g < nwords && a.mask_bits) {
+            w = reinterpret_cast<const uint32_t *>(row)[g];
+        } else if (g < nwords) {
             const uint64_t *p8 = reinterpret_cast<const uint64_t *>(row + 32 * g);      // rows are 128 B aligned and padded
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
     if (lane == 0) e0 = atomicAdd(&f.counters[1], n);
     e0 = __shfl_sync(kAll, e0, 0);
     if (e0 + n > f.edge_capacity) { if (lane == 0) f.counters[2] = 1; if (lane < P) score[lane] = 0.0; return; }
-    if (lane == 0) { f.node_edge0[target] = e0; f.node_nedge[target] = n; }
+    if (lane == 0) { f.node_edge0[target] = e0; f.node_nedge[target] = n; f.node_sum_n[target] = 0.0; }
     int e = e0 + incl - mine;
     const double uni = n > 0 ? __ddiv_rn(1.0, static_cast<double>(n)) : 0.0;
     for (int j = 0; j < rounds; ++j) {
@@ -199,6 +200,7 @@ __global__ void puct_backup_kernel(blk_puct_forest f) {
     if (t >= f.num_trees) return;
     const double *score = f.scores + static_cast<int64_t>(t) * f.num_players;
     const int32_t *path = f.path + static_cast<int64_t>(t) * f.max_depth;
+    const int32_t *pnode = f.path_node + static_cast<int64_t>(t) * f.max_depth;
     for (int d = f.path_len[t] - 1; d >= 0; --d) {
         const int e = path[d];
         const int child = f.edge_child[e];
@@ -207,6 +209,7 @@ __global__ void puct_backup_kernel(blk_puct_forest f) {
         const double n = f.edge_n[e], q = f.edge_q[e];
         f.edge_q[e] = __ddiv_rn(__dadd_rn(__dmul_rn(n, q), val), __dadd_rn(n, 1.0));
         f.edge_n[e] = __dadd_rn(n, 1.0);
+        f.node_sum_n[pnode[d]] = __dadd_rn(f.node_sum_n[pnode[d]], 1.0);     // integer-valued: exact
     }
     if (t == 0) f.counters[4] += f.num_trees;      // this simulation's B pool slots are taken (expand has finished)
 }
@@ -292,6 +295,7 @@ int blk_puct_expand(const blk_puct_forest *f, const blk_puct_expand_args *x, voi
     ExpandArgs a;
     a.f = *f; a.new_slot_base = x->new_slot_base; a.state_words = x->state_words; a.meta_word = x->meta_word;
     a.attach_only = x->attach_only; a.new_states = x->new_states; a.pool = x->pool; a.mask = x->mask; a.flags = x->flags;
+    a.mask_bits = x->mask_bits; a.mask_stride_words = x->mask_stride_words;
     a.terminal = x->terminal; a.prior = x->prior; a.prior_dtype = x->prior_dtype; a.prior_stride = x->prior_stride;
     a.value = x->value;
     const int grid = (f->num_trees + kWarpsPerBlock - 1) / kWarpsPerBlock;

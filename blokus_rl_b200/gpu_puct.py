@@ -47,6 +47,7 @@ class GpuPuct:
             "leaf_node": torch.zeros(self.B, **i32), "leaf_edge": torch.zeros(self.B, **i32),
             "src_slot": torch.zeros(self.B, **i32), "step_action": torch.zeros(self.B, **i32),
             "scores": torch.zeros((self.B, self.P), **f64), "counters": torch.zeros(5, **i32),
+            "node_sum_n": torch.empty(self.node_cap, **f64), "path_node": torch.empty((self.B, max_depth), **i32),
         }
         self.pool = torch.empty((self.node_cap, engine.state_words), dtype=torch.int32, device=dev)
         self.used = 0
@@ -55,8 +56,11 @@ class GpuPuct:
                                              "node_edge0", "node_nedge", "node_state", "node_mover", "node_terminal",
                                              "node_term_value", "edge_action", "edge_child", "edge_n", "edge_q", "edge_p",
                                              "root", "path", "path_len", "status", "leaf_node", "leaf_edge", "src_slot",
-                                             "step_action", "scores", "counters")])
-        self.buf = engine.make_buffers(self.B, "bytes")
+                                             "step_action", "scores", "counters", "node_sum_n", "path_node")])
+        # a net needs the dense bool mask; the uniform prior only needs the legal ids, which the 8x smaller
+        # bit-packed mask gives just as well
+        self.mask_fmt = "bits" if isinstance(self.evaluator, UniformEvaluator) else "bytes"
+        self.buf = engine.make_buffers(self.B, self.mask_fmt)
         self.stage = torch.empty((self.B, engine.state_words), dtype=torch.int32, device=dev)   # blk_step output
         self.use_cuda_graph = use_cuda_graph and getattr(self.evaluator, "graph_safe", False)
         self._graphs: dict = {}         # (cpuct, epsilon_fix) -> captured simulation
@@ -84,6 +88,7 @@ class GpuPuct:
         t["node_state"][:B] = ar
         t["node_edge0"][:B] = -1
         t["node_nedge"][:B] = 0
+        t["node_sum_n"][:B] = 0
         t["node_mover"][:B] = (states[:, self._meta] & 15).to(torch.int8)
         t["node_terminal"][:B] = (flags & 1).to(torch.int8)
         t["node_term_value"][:B] = term.to(torch.float64)
@@ -96,8 +101,8 @@ class GpuPuct:
         device-side counter), so the sequence can be captured into a CUDA graph."""
         t, B, eng = self.t, self.B, self.eng
         src = self.pool.index_select(0, t["src_slot"].long())
-        out = eng.step(src, t["step_action"], out_states=self.stage, buffers=self.buf, mask="bytes", want_count=False,
-                       want_scores=False)
+        out = eng.step(src, t["step_action"], out_states=self.stage, buffers=self.buf, mask=self.mask_fmt,
+                       want_count=False, want_scores=False)
         prior, pd, ps, value = None, 0, 0, None
         if not attach_only and not isinstance(self.evaluator, UniformEvaluator):
             p, v = self.evaluator.evaluate(eng, self.stage, out.mask)
@@ -108,7 +113,8 @@ class GpuPuct:
             ps = prior.stride(0)
             value = v.to(torch.float64).contiguous()
         args = _lib.BlkPuctExpandArgs(-1, eng.state_words, self._meta, int(attach_only), self.stage.data_ptr(),
-                                      self.pool.data_ptr(), out.mask_raw.data_ptr(), out.flags.data_ptr(),
+                                      self.pool.data_ptr(), out.mask_raw.data_ptr(), int(self.mask_fmt == "bits"),
+                                      eng.mask_words, out.flags.data_ptr(),
                                       out.terminal.data_ptr(), None if prior is None else prior.data_ptr(), pd, ps,
                                       None if value is None else value.data_ptr())
         self._check(self._lib.blk_puct_expand(C.byref(self.forest), C.byref(args), self._stream()))

@@ -174,6 +174,8 @@ typedef struct {
     int32_t *step_action;         /* [B] action for blk_step (BLK_ACTION_NONE: evaluate the state as it is) */
     double *scores;               /* [B][P] score vector of the current simulation */
     int32_t *counters;            /* [5] nodes used, edges used, capacity overflow flag, illegal-action flag, pool slots used */
+    double *node_sum_n;           /* [nodes] sum of the node's edge visit counts (the N.sum() of mcts.py:43) */
+    int32_t *path_node;           /* [B][max_depth] node of each path edge */
 } blk_puct_forest;
 
 typedef struct {
@@ -183,7 +185,9 @@ typedef struct {
     int32_t attach_only;          /* 1: only create the requested child nodes and make them the roots (blk_puct_advance) */
     const uint32_t *new_states;   /* [B][state_words] */
     uint32_t *pool;               /* nullable: state pool; the new states are copied to slots base + t */
-    const uint8_t *mask;          /* [B][mask_stride] */
+    const uint8_t *mask;          /* [B][mask_stride] byte masks, or bit-packed rows when mask_bits = 1 */
+    int32_t mask_bits;            /* 1: mask holds uint32 words, mask_stride_words per row (uniform prior: no net needs bytes) */
+    int32_t mask_stride_words;
     const uint8_t *flags;         /* [B] */
     const float *terminal;        /* [B][P] */
     const void *prior;            /* [B][prior_stride] or NULL */
