@@ -22,7 +22,10 @@ from .mcts import UniformEvaluator
 
 class GpuPuct:
     def __init__(self, engine, evaluator=None, num_trees: int = 256, max_simulations: int = 4096,
-                 mean_edges_per_node: int = 256, max_depth: int = 96, use_cuda_graph: bool = True):
+                 mean_edges_per_node: int = 384, max_depth: int = 96, use_cuda_graph: bool = True):
+        """``max_simulations`` bounds nodes per tree (one per simulation + roots); ``mean_edges_per_node`` sizes the
+        edge arrays (32 B per edge; 20x20 positions have 58-760 legal moves, ~170 on average over a game and
+        300-450 around plies 8-24).  Overflow is detected on the device and reported by :meth:`check`."""
         self.eng = engine
         self.evaluator = evaluator or UniformEvaluator()
         self.B, self.P, self.A = num_trees, engine.num_players, engine.num_actions

@@ -71,14 +71,14 @@ def self_play_batched(engine, evaluator=None, num_games: int = 8, num_mcts_sims:
 
 def self_play_gpu(engine, evaluator=None, num_games: int = 256, num_mcts_sims: int = 25, cpuct: float = 1.0,
                   temperature: float = 1.0, dirichlet_alpha: float = 1.0, dirichlet_weight: float = 0.25,
-                  rng: np.random.Generator | None = None, max_plies: int = 4 * 21 + 1):
+                  rng: np.random.Generator | None = None, max_plies: int = 4 * 21 + 1, mean_edges_per_node: int = 384):
     """Same contract as :func:`self_play_batched`, with the search trees resident on the GPU
     (:class:`blokus_rl_b200.gpu_puct.GpuPuct`): the host only samples one move per game per ply."""
     from .gpu_puct import GpuPuct
     rng = rng or np.random.default_rng()
     A, P = engine.num_actions, engine.num_players
     search = GpuPuct(engine, evaluator or UniformEvaluator(), num_trees=num_games,
-                     max_simulations=(num_mcts_sims + 1) * max_plies + 2)
+                     max_simulations=(num_mcts_sims + 1) * max_plies + 2, mean_edges_per_node=mean_edges_per_node)
     search.set_roots(engine.new_states(num_games))
     data: list[list] = [[] for _ in range(num_games)]
     done = np.zeros(num_games, bool)
