@@ -13,9 +13,9 @@ _PKG = Path(__file__).resolve().parent
 import os as _os
 LIB_PATH = Path(_os.environ.get("BLOKUS_B200_LIB", _PKG / "libblokus_b200.so"))   # override: A/B kernel experiments only
 
-BLK_MASK_NONE, BLK_MASK_BITS, BLK_MASK_BYTES = 0, 1, 2
+BLK_MASK_NONE, BLK_MASK_BITS, BLK_MASK_BYTES, BLK_MASK_INDICES = 0, 1, 2, 3
 BLK_OPT_AUTO_RESET = 1
-BLK_FLAG_DONE, BLK_FLAG_ILLEGAL = 1, 2
+BLK_FLAG_DONE, BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED = 1, 2, 4
 ABI_VERSION = 1
 
 EXPORTS = (

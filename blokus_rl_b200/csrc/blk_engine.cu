@@ -389,7 +389,7 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     int &cur_max = s_max_smem[cfg->device & 15][geom];
     if (h->step_smem > cur_max) {
         cudaError_t err = cudaFuncSetAttribute(h->ks.rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, h->roll_smem);
-        for (int f = 0; f < 4 && err == cudaSuccess; ++f)
+        for (int f = 0; f < 5 && err == cudaSuccess; ++f)
             for (int sm = 0; sm < 2 && err == cudaSuccess; ++sm)
                 err = cudaFuncSetAttribute(h->ks.step[f][sm], cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
         if (err != cudaSuccess) { blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed"); }
@@ -453,14 +453,18 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
         if (!args->mask) return fail(BLK_ERR_ARG, "mask_format set but mask is NULL");
         if (args->mask_format == BLK_MASK_BITS && args->mask_stride < h->g.mw) return fail(BLK_ERR_ARG, "mask_stride < mask_words");
         if (args->mask_format == BLK_MASK_BYTES && args->mask_stride < h->g.A) return fail(BLK_ERR_ARG, "mask_stride < num_actions");
-        if (args->mask_format != BLK_MASK_BITS && args->mask_format != BLK_MASK_BYTES) return fail(BLK_ERR_ARG, "unknown mask_format");
+        if (args->mask_format != BLK_MASK_BITS && args->mask_format != BLK_MASK_BYTES && args->mask_format != BLK_MASK_INDICES)
+            return fail(BLK_ERR_ARG, "unknown mask_format");
+        if (args->mask_format == BLK_MASK_INDICES && (!args->legal_count || args->mask_stride < 1))
+            return fail(BLK_ERR_ARG, "BLK_MASK_INDICES needs legal_count and a positive mask_stride");
     }
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     KParams kp;
     kp.a = *args; kp.tables = h->d_tables; kp.t = h->t; kp.g = h->g;
     kp.queue = h->d_queue + 2 * (h->launch_seq++ % kQueueSlots);
     const int grid = grid_for(args->n, kWarps, h->sm_count, h->step_blocks_per_sm);
-    int variant = args->mask_format;                  // 0 none, 1 bits, 2 bytes (vector stores), 3 bytes (unaligned buffer)
+    int variant = args->mask_format;                  // 0 none, 1 bits, 2 bytes (vector stores), 3 bytes (unaligned buffer), 4 ids
+    if (variant == BLK_MASK_INDICES) variant = 4;
     if (variant == BLK_MASK_BYTES &&
         ((args->mask_stride & 15) != 0 || (reinterpret_cast<uintptr_t>(args->mask) & 15) != 0 || args->mask_stride < h->g.mask_bytes))
         variant = 3;

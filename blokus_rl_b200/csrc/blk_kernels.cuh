@@ -507,7 +507,8 @@ __device__ __forceinline__ float terminal_value(const EnvRegs &e, const Dims &g,
 // ---------------------------------------------------------------------------------------------
 // step / legal-mask kernel
 // ---------------------------------------------------------------------------------------------
-// kFmt: 0 = no mask output, 1 = bit-packed, 2 = bytes through 16 B vector stores, 3 = bytes into an unaligned buffer.
+// kFmt: 0 = no mask output, 1 = bit-packed, 2 = bytes through 16 B vector stores, 3 = bytes into an unaligned buffer,
+//       4 = ascending list of legal ids (uint16).
 template <int kN, int kP, int kFmt, bool kSample>
 __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const KParams kp) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -626,6 +627,8 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
             unsigned char *urow = reinterpret_cast<unsigned char *>(a.mask) + env * mstride;     // kFmt == 3 only
             const int ush = static_cast<int>(reinterpret_cast<uintptr_t>(urow) & 15);
             uint32_t uprev = 0u;
+            uint16_t *irow = reinterpret_cast<uint16_t *>(a.mask) + env * mstride;                // kFmt == 4 only
+            int ibase = 0;
 #pragma unroll(kEmitUnroll)
             for (int r = 0; r < (kN == 20 ? 30 : rounds); ++r) {
                 uint32_t word;
@@ -639,7 +642,22 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                 } else {
                     cnt += pc;
                 }
-                if (kFmt == 1) {
+                if (kFmt == 4) {
+                    // sparse form: ids of the set bits in ascending order.  Lane l's word precedes lane l+1's, so an
+                    // exclusive scan of the per-lane popcounts gives every lane its slot range in this pass.
+                    if (__any_sync(kAllLanes, pc != 0)) {          // most 1,024-bit passes of a 0.6 % dense mask are empty
+                        const int incl = warp_incl_scan(pc, lane);
+                        int slot = ibase + incl - pc;
+                        uint32_t w = word;
+                        while (w) {
+                            const int id = (((r << 5) + lane) << 5) + __ffs(w) - 1;
+                            w &= w - 1;
+                            if (slot < mstride) irow[slot] = static_cast<uint16_t>(id);
+                            ++slot;
+                        }
+                        ibase += __shfl_sync(kAllLanes, incl, 31);
+                    }
+                } else if (kFmt == 1) {
                     if (r < (kN == 20 ? 29 : rounds - 1) || (r << 5) + lane < mw) wrow[r << 5] = word;
                 } else if (kFmt == 2) {
                     // 32 words -> 1024 bytes; each lane expands 16 bits through the byte LUT (two 8-byte entries) and
@@ -683,6 +701,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                 }
             }
             if (!kSample) cnt = warp_sum(cnt);
+            if (kFmt == 4 && cnt > mstride) flags |= BLK_FLAG_TRUNCATED;
         }
         if (want_count && lane == 0) a.legal_count[env] = cnt;
 
@@ -872,7 +891,7 @@ __global__ void __launch_bounds__(kRollWarps * 32, BLK_ROLL_MIN_BLOCKS) rollout_
 using StepFn = void (*)(const KParams);
 using RolloutFn = void (*)(const RParams);
 struct KernelSet {
-    StepFn step[4][2];      // [mask format variant: none, bits, bytes (vector stores), bytes (unaligned)][sampler]
+    StepFn step[5][2];      // [mask format variant: none, bits, bytes (vector stores), bytes (unaligned), ids][sampler]
     RolloutFn rollout;
 };
 template <int kN, int kP>
@@ -882,6 +901,7 @@ inline KernelSet make_kernel_set() {
     k.step[1][0] = step_kernel<kN, kP, 1, false>; k.step[1][1] = step_kernel<kN, kP, 1, true>;
     k.step[2][0] = step_kernel<kN, kP, 2, false>; k.step[2][1] = step_kernel<kN, kP, 2, true>;
     k.step[3][0] = step_kernel<kN, kP, 3, false>; k.step[3][1] = step_kernel<kN, kP, 3, true>;
+    k.step[4][0] = step_kernel<kN, kP, 4, false>; k.step[4][1] = step_kernel<kN, kP, 4, true>;
     k.rollout = rollout_kernel<kN, kP>;
     return k;
 }

@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import (BLK_FLAG_DONE, BLK_FLAG_ILLEGAL, BLK_MASK_BITS, BLK_MASK_BYTES, BLK_MASK_NONE,
+from ._lib import (BLK_FLAG_DONE, BLK_FLAG_ILLEGAL, BLK_MASK_BITS, BLK_MASK_BYTES, BLK_MASK_INDICES, BLK_MASK_NONE,
                    BLK_OPT_AUTO_RESET, EngineError)
 
 __all__ = ["BlokusEngine", "StepOut", "RolloutOut", "EngineError", "BLK_FLAG_DONE", "BLK_FLAG_ILLEGAL"]
@@ -70,6 +70,7 @@ class BlokusEngine:
         self.num_actions, self.state_words = info.num_actions, info.state_words
         self.mask_words, self.mask_bytes = info.mask_words, info.mask_bytes
         self.sm_count = info.sm_count
+        self.max_legal = 1024        # row width of the sparse 'indices' mask format (no reachable position is known to exceed ~800)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -118,7 +119,9 @@ class BlokusEngine:
             return torch.empty((n, self.mask_bytes), dtype=torch.uint8, device=self.device)
         if fmt == "bits":
             return torch.empty((n, self.mask_words), dtype=torch.int32, device=self.device)
-        raise ValueError("fmt must be 'bytes' or 'bits'")
+        if fmt == "indices":      # ascending legal ids (uint16 carried as int16), legal_count[i] valid entries per row
+            return torch.empty((n, self.max_legal), dtype=torch.int16, device=self.device)
+        raise ValueError("fmt must be 'bytes', 'bits' or 'indices'")
 
     def mask_view(self, raw: torch.Tensor) -> torch.Tensor:
         """bool [n, A] view of a raw byte-mask buffer (what torch.masked_select consumes,
@@ -152,8 +155,11 @@ class BlokusEngine:
                 fmt, stride = BLK_MASK_BITS, raw_mask.stride(0)
             elif raw_mask.dtype in (torch.uint8, torch.bool):
                 fmt, stride = BLK_MASK_BYTES, raw_mask.stride(0)
+            elif raw_mask.dtype == torch.int16:
+                fmt, stride = BLK_MASK_INDICES, raw_mask.stride(0)
+                want_count = True
             else:
-                raise ValueError("mask buffer must be uint8/bool (bytes) or int32 (bits)")
+                raise ValueError("mask buffer must be uint8/bool (bytes), int32 (bits) or int16 (indices)")
             if raw_mask.shape[0] != n or raw_mask.stride(1) != 1:
                 raise ValueError("mask buffer must have n rows with unit column stride")
             if fmt == BLK_MASK_BYTES and raw_mask.shape[1] < self.num_actions:

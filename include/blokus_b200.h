@@ -41,7 +41,10 @@ typedef enum {
     BLK_ERR_NODEV = -3     /* no usable sm_100 device */
 } blk_status;
 
-typedef enum { BLK_MASK_NONE = 0, BLK_MASK_BITS = 1, BLK_MASK_BYTES = 2 } blk_mask_format;
+/* BLK_MASK_INDICES: the sparse form of the same mask -- the ascending legal action ids as uint16 (the list the
+ * reference's PPO path reads per env: envs.get_attr("ai_possible_indexes"), blokus_rl/ppo/trainer.py:385);
+ * legal_count[i] says how many entries of row i are valid (it is required in this format). */
+typedef enum { BLK_MASK_NONE = 0, BLK_MASK_BITS = 1, BLK_MASK_BYTES = 2, BLK_MASK_INDICES = 3 } blk_mask_format;
 
 /* score_rule: 0 = squares placed (default); 1 = squares placed + 15 when all 21 pieces are placed,
  * + 5 more when the monomino went last (SURVEY.md Appendix A, R10 is OPEN in the reference). */
@@ -69,7 +72,7 @@ typedef struct blk_engine blk_engine;
 
 enum { BLK_OPT_AUTO_RESET = 1 };
 #define BLK_ACTION_NONE (-1)   /* per-env "do not move": the env only gets its mask / status refreshed */
-enum { BLK_FLAG_DONE = 1, BLK_FLAG_ILLEGAL = 2 };
+enum { BLK_FLAG_DONE = 1, BLK_FLAG_ILLEGAL = 2, BLK_FLAG_TRUNCATED = 4 };
 
 /* Arguments of blk_step().  Every pointer is a DEVICE pointer; nullable ones are marked. */
 typedef struct {
@@ -79,8 +82,9 @@ typedef struct {
     const int32_t *action;      /* [n] action ids (BLK_ACTION_NONE = skip this env); NULL = no env moves: mask only */
     void *mask;                 /* nullable; next mover's legal mask */
     int32_t mask_format;        /* blk_mask_format */
-    int64_t mask_stride;        /* row stride: uint32 words for BITS (>= mask_words), bytes for BYTES
-                                   (>= num_actions; multiple of 16 with a 16 B aligned base) */
+    int64_t mask_stride;        /* row stride: uint32 words for BITS (>= mask_words); bytes for BYTES (>= num_actions;
+                                   fastest when a multiple of 16 with a 16 B aligned base); uint16 entries for INDICES
+                                   (rows with more legal actions than that are truncated and flagged) */
     int32_t *legal_count;       /* nullable [n]; number of legal actions of the next mover */
     float *terminal;            /* nullable [n][P]; 3 / 1 / -1 terminal vector when the step ended the game, else 0 */
     uint8_t *flags;             /* nullable [n]; BLK_FLAG_* */

@@ -18,6 +18,7 @@ class OracleEngine:
         self.mask_bytes = (self.num_actions + 127) // 128 * 128
         self.mask_words = ((self.num_actions + 31) // 32 + 3) // 4 * 4
         self.device = torch.device("cpu")
+        self.max_legal = 1024
 
     def _unpack(self, states):
         w = states.numpy().view(np.uint32)
@@ -67,14 +68,24 @@ class OracleEngine:
         if sample:
             nxt = torch.tensor([orc.sample_action(s, seed, env_id_base + i) for i, s in enumerate(sts)], dtype=torch.int32)
         mt = None
-        if mask == "bytes" or (isinstance(mask, torch.Tensor) and mask.dtype != torch.int32):
-            mt = torch.from_numpy(m.astype(bool))
-            if isinstance(mask, torch.Tensor):
-                mask[:, : self.num_actions] = torch.from_numpy(m).to(mask.dtype)
-        elif mask == "bits" or isinstance(mask, torch.Tensor):
+        is_t = isinstance(mask, torch.Tensor)
+        if mask == "indices" or (is_t and mask.dtype == torch.int16):
+            ids = np.zeros((n, self.max_legal), np.int16)
+            for i in range(n):
+                nz = np.flatnonzero(m[i])
+                if len(nz) > self.max_legal:
+                    flags[i] |= 4
+                nz = nz[: self.max_legal]
+                ids[i, : len(nz)] = nz.astype(np.uint16).view(np.int16)
+            mt = torch.from_numpy(ids)
+        elif mask == "bits" or (is_t and mask.dtype == torch.int32):
             bits = np.zeros((n, self.mask_words * 32), np.uint8)
             bits[:, : self.num_actions] = m
             mt = torch.from_numpy(np.packbits(bits, axis=1, bitorder="little").view(np.int32).copy())
+        elif mask == "bytes" or is_t:
+            mt = torch.from_numpy(m.astype(bool))
+            if is_t:
+                mask[:, : self.num_actions] = torch.from_numpy(m).to(mask.dtype)
         return StepOut(out_states, mt, torch.from_numpy(m.sum(1).astype(np.int32)), torch.from_numpy(term),
                        torch.from_numpy(flags), torch.from_numpy(scores), nxt, None)
 

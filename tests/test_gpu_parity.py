@@ -241,3 +241,29 @@ def test_plain_c_program_runs(tmp_path):
     subprocess.check_call(cmd)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "c_abi_smoke ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_sparse_index_mask_format(engine20, engine7, oracle20):
+    """BLK_MASK_INDICES: ascending legal ids (the reference's ai_possible_indexes lists) == nonzero of the dense mask."""
+    import torch
+    for eng in (engine20, engine7):
+        n = 300
+        s = eng.new_states(n)
+        out = eng.step(s, None, mask="bytes", sample=True, seed=4)
+        for _ in range(16 if eng.board_size == 20 else 4):
+            out = eng.step(s, out.next_action, mask="bytes", sample=True, seed=4)
+        sparse = eng.step(s, None, mask="indices")
+        torch.cuda.synchronize()
+        ids = sparse.mask.cpu().numpy().view(np.uint16)
+        cnt = sparse.legal_count.cpu().numpy()
+        dense = out.mask.cpu().numpy()
+        assert ids.shape == (n, eng.max_legal) and (sparse.flags & 4).sum() == 0
+        for i in range(n):
+            assert ids[i, : cnt[i]].tolist() == np.flatnonzero(dense[i]).tolist()
+    # truncation is flagged, never silent: a 16-entry row cannot hold the 58 first moves
+    s = engine20.new_states(2)
+    small = torch.zeros((2, 16), dtype=torch.int16, device=s.device)
+    o2 = engine20.step(s, None, mask=small)
+    first = np.flatnonzero(oracle20.legal_mask(oracle20.new_state()))
+    assert (o2.flags.cpu().numpy() & 4).all() and (o2.legal_count.cpu().numpy() == 58).all()
+    assert small[0].cpu().numpy().view(np.uint16).tolist() == first[:16].tolist()
