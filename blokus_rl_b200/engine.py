@@ -149,7 +149,14 @@ class BlokusEngine:
         if isinstance(mask, torch.Tensor):
             raw_mask = mask
         elif mask is not None:
-            raw_mask = b.mask_raw if b is not None and getattr(b, "mask_raw", None) is not None else self.alloc_mask(n, mask)
+            want_dtype = {"bytes": torch.uint8, "bits": torch.int32, "indices": torch.int16}.get(mask)
+            if want_dtype is None:
+                raise ValueError("mask must be 'bytes', 'bits', 'indices', a tensor or None")
+            raw_mask = b.mask_raw if b is not None and getattr(b, "mask_raw", None) is not None else None
+            if raw_mask is not None and raw_mask.dtype != want_dtype:
+                raise ValueError(f"buffers hold a {raw_mask.dtype} mask but mask={mask!r} was requested")
+            if raw_mask is None:
+                raw_mask = self.alloc_mask(n, mask)
         if raw_mask is not None:
             if raw_mask.dtype == torch.int32:
                 fmt, stride = BLK_MASK_BITS, raw_mask.stride(0)
