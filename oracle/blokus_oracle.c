@@ -4,12 +4,19 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library; the product path (blokus_rl_b200) never does.
  *
- * PARITY UNPINNED.  The reference's env arithmetic lives in two un-vendored, un-pinned git
+ * PARITY PINNED ONLY ON THE REFERENCE'S RENDERED GAMES; everything those renders do not show is
+ * UNPINNED.  The reference's env arithmetic lives in two un-vendored, un-pinned git
  * dependencies (colosseumrl: /root/reference/setup.py:11; blokus-gym: setup.py:33) that are
  * absent from /root/reference and from this image, and the reference has no tests
- * (.github/workflows/analysis.yml:10-57 is lint only).  This file therefore restates the
- * *contract* visible at the reference's call sites plus standard Blokus rules (SURVEY.md
- * Appendix A, rules R1-R13):
+ * (.github/workflows/analysis.yml:10-57 is lint only).  The only outputs of the real engine in
+ * /root/reference are the renders under docs/images: three complete games (80 transitions), two
+ * positions and one observation; tests/golden/make_ref_render_golden.py decodes them and
+ * tests/test_ref_render_golden.py replays them here (legality of every reference move, side to
+ * move incl. auto-skips, game end at the last frame and not before, winners vs the file names,
+ * start corners, observation planes).  Not shown by the renders and therefore still unpinned:
+ * action-id order / action strings, score bonuses, observation orientation for movers 1..3.
+ * This file restates the *contract* visible at the reference's call sites plus standard Blokus
+ * rules (rules R1-R13):
  *   new_state      blokus_rl/colossumrl/blokus_wrapper.py:80-87     -> orc_reset
  *   next_state     blokus_wrapper.py:89-106                          -> orc_step
  *   valid_actions  blokus_wrapper.py:108-132, 233-246                -> orc_legal_mask

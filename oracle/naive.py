@@ -1,6 +1,6 @@
 """Pure-Python, set-based Blokus rules.  TEST INFRASTRUCTURE ONLY (third, slowest oracle).
 
-PARITY UNPINNED: the reference env (colosseumrl / blokus-gym, /root/reference/setup.py:11,33) is
+Parity pinned only on the reference's rendered games (tests/test_ref_render_golden.py): the reference env (colosseumrl / blokus-gym, /root/reference/setup.py:11,33) is
 absent; this restates SURVEY.md Appendix A rules R1-R11 at the level of cell sets, with its own
 polyomino enumeration (it does NOT import blokus_rl_b200.tables), so that it can check both the C
 oracle and the table generator.  Small cases only.

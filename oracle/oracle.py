@@ -1,7 +1,8 @@
 """ctypes front-end of the C oracle (oracle/blokus_oracle.c).  TEST INFRASTRUCTURE ONLY.
 
-Imported only by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.  PARITY UNPINNED
-(see the header of blokus_oracle.c).
+Imported only by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.  Parity is pinned only on
+the reference's rendered games (tests/test_ref_render_golden.py); see the header of blokus_oracle.c for what stays
+unpinned.
 """
 from __future__ import annotations
 
