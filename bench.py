@@ -29,6 +29,18 @@ UNIT = "steps/s"
 ALG_BYTES = {"bytes": 31154, "bits": 4529}     # SURVEY.md section 8d / DESIGN.md: algorithmic HBM bytes per env step
 
 
+def alg_bytes(fmt: str, N: int, P: int, A: int) -> int:
+    """Algorithmic HBM bytes of one env step: state read + write, action, reward/done/score, mask."""
+    if (N, P) == (20, 4):
+        return ALG_BYTES[fmt]
+    state = 4 * (P * N + P + 4)
+    return 2 * state + 4 + 13 + (A if fmt == "bytes" else 4 * ((A + 31) // 32))
+
+
+def metric_name(N: int, P: int) -> str:
+    return f"env steps/s w/ legal masks ({N}x{N} {P}p)"
+
+
 def host_cores() -> int:
     return len(os.sched_getaffinity(0))
 
@@ -36,11 +48,11 @@ def host_cores() -> int:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (oracle/blokus_oracle.c, bit-parallel variant) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_random_play(total_plies: int, threads: int, seed: int = 0x5EED):
+def cpu_random_play(total_plies: int, threads: int, seed: int = 0x5EED, N: int = 20, P: int = 4):
     """Uniform-random legal play with full byte masks on `threads` host threads (ctypes releases the GIL).
     Returns (plies, seconds)."""
     from oracle.oracle import Oracle
-    orc = Oracle(20, 4)
+    orc = Oracle(N, P)
     per = max(1, total_plies // threads)
     states = [orc.new_state() for _ in range(threads)]
     done = [0] * threads
@@ -61,15 +73,16 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    per_step = 256 * cores                       # bounded sample: 256 plies per core per "step"
-    cpu_random_play(per_step * max(1, args.warmup), cores)
-    plies, secs = cpu_random_play(per_step * args.steps, cores)
+    N, P = args.board, args.players
+    per_step = (256 if N >= 20 else 4096) * cores      # bounded sample: 256 plies (20x20) per core per "step"
+    cpu_random_play(per_step * max(1, args.warmup), cores, N=N, P=P)
+    plies, secs = cpu_random_play(per_step * args.steps, cores, N=N, P=P)
     v = plies / secs
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(N, P), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "Blokus 20x20 4-player random-legal play with full byte masks, CPU",
+        "config": {"workload": f"Blokus {N}x{N} {P}-player random-legal play with full byte masks, CPU",
                    "note": "the reference env engine (colosseumrl) is an absent un-vendored dependency; this arm times "
                            "this repo's C restatement (oracle port, bit-parallel variant), one env per host thread"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -146,7 +159,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    eng = BlokusEngine(20, 4, device=dev)
+    N, P = args.board, args.players
+    headline = (N, P) == (20, 4)
+    eng = BlokusEngine(N, P, device=dev)
+    AB = alg_bytes(args.mask, N, P, eng.num_actions)
     n, fmt, seed = args.envs, args.mask, 0x5EED
     base = rank * n                                  # global env ids: results are partition-invariant
     states = eng.new_states(n)
@@ -200,7 +216,7 @@ def run_ours(args):
         halves.append({
             "states": st, "buf": b, "stream": torch.cuda.Stream(device=dev), "event": torch.cuda.Event(),
             "h_act": torch.empty(nh, dtype=torch.int32).pin_memory(), "h_flags": torch.empty(nh, dtype=torch.uint8).pin_memory(),
-            "h_term": torch.empty((nh, 4), dtype=torch.float32).pin_memory(), "base": base + k * nh})
+            "h_term": torch.empty((nh, P), dtype=torch.float32).pin_memory(), "base": base + k * nh})
         halves[-1]["h_act"].copy_(b.next_action)
     e2e_steps = max(4, min(args.steps, 512))
     sync_all()
@@ -249,37 +265,37 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     mean_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
-    achieved = ALG_BYTES[fmt] * n / (mean_launch_ms * 1e-3) / 1e9
+    achieved = AB * n / (mean_launch_ms * 1e-3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
-        traffic = json.loads(tf.read_text()).get(f"step_kernel_{fmt}_{n}")
+        traffic = json.loads(tf.read_text()).get(f"step_kernel_{fmt}_{n}" if headline else f"step_kernel_{N}_{P}_{fmt}_{n}")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(N, P), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"Blokus 20x20 4-player batched env: step + full legal mask ({fmt}) + on-device random "
-                               f"policy, {n} envs per GPU, auto-reset (BASELINE.json configs[1])",
+        "config": {"workload": f"Blokus {N}x{N} {P}-player batched env: step + full legal mask ({fmt}) + on-device random "
+                               f"policy, {n} envs per GPU, auto-reset" + (" (BASELINE.json configs[1])" if headline and n == 65536 else ""),
                    "envs_per_gpu": n, "mask_format": fmt, "parallelism": f"env-sharded x{world}, no hot-path collective",
-                   "l2": f"per-step working set {(ALG_BYTES[fmt] * n) / 1e6:.0f} MB vs 126 MB L2"
-                         + (" (mask writes evict it every step)" if fmt == "bytes" else " (< L2: states stay L2-resident; see DESIGN.md)")},
+                   "l2": f"per-step working set {(AB * n) / 1e6:.0f} MB vs 126 MB L2"
+                         + (" (mask writes evict it every step)" if AB * n > 2 * 126e6 else " (not larger than L2: states stay L2-resident; see DESIGN.md)")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n * world,
-                "d2h_bytes_per_step": (4 + 1 + 16) * n * world, "steps": e2e_steps,
+                "d2h_bytes_per_step": (4 + 1 + 4 * P) * n * world, "steps": e2e_steps,
                 "note": f"pinned host actions H2D -> blk_step -> sampled actions, flags, terminal vectors D2H, host sync before the next actions; {H} half-batches pipelined on {H} streams; masks stay on the device for the policy net"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "step_kernel",
-                     "alg_bytes_per_step": ALG_BYTES[fmt], "mean_launch_ms": mean_launch_ms},
+                     "alg_bytes_per_step": AB, "mean_launch_ms": mean_launch_ms},
         "clocks": clocks,
         "counters": {"steps": int(ctr[0]), "games_finished_last_step": int(ctr[1]), "illegal": int(ctr[2])},
     }
-    if world == 1 and not args.no_extra:
+    if world == 1 and not args.no_extra and headline:
         line["extra"] = extra_workloads(eng, torch)
     if world == 1 and not args.no_cpu:
         cores = host_cores()
         target = 12.0                                         # seconds of CPU work
-        p1, s1 = cpu_random_play(2000 * cores, cores)
-        plies, secs = cpu_random_play(int(p1 / s1 * target), cores)
+        p1, s1 = cpu_random_play(2000 * cores, cores, N=N, P=P)
+        plies, secs = cpu_random_play(int(p1 / s1 * target), cores, N=N, P=P)
         from oracle.oracle import Oracle
         o7 = Oracle(7, 2)
         s7 = o7.new_state()
@@ -287,7 +303,7 @@ def run_ours(args):
         n7, _, _ = o7.random_play(s7, 0, 0, 20000, auto_reset=True, fast=True, log=False)
         line.setdefault("extra", {})["cpu_7x7_2p_single_env_plies_per_s"] = n7 / (time.perf_counter() - t7)   # BASELINE configs[0]
         line["cpu_baseline"] = {"value": plies / secs, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{plies} plies of 20x20 4p random-legal play with full byte masks, one env per "
+                                "sample": f"{plies} plies of {N}x{N} {P}p random-legal play with full byte masks, one env per "
                                           f"host thread, {secs:.1f} s (oracle port, bit-parallel variant)"}
     print(json.dumps(line))
     if world > 1:
@@ -319,6 +335,21 @@ def extra_workloads(eng, torch):
     extra = {"mcts_rollouts_per_s": 1024 * 1024 / sec, "rollout_plies_per_s": 1024 * 1024 * plies / sec,
              "rollout_workload": "1024 roots after 24 random plies x 1024 uniform-random playouts to terminal",
              "rollout_mean_plies": plies}
+    # SURVEY 8d workload 2: reset, mask and step kernels separately (the headline is the fused step + mask + sampler)
+    E = 65536
+    st = eng.new_states(E)
+    o = eng.step(st, None, mask=None, sample=True, seed=11)
+    for _ in range(16):
+        o = eng.step(st, o.next_action, mask=None, sample=True, seed=11, auto_reset=True)
+    mb = eng.make_buffers(E, "bytes")
+    scratch_states = eng.new_states(E)
+    extra["reset_states_per_s"] = E / timed(lambda: eng.reset(scratch_states), 20)
+    extra["legal_mask_only_bytes_per_s"] = E / timed(lambda: eng.step(st, None, buffers=mb, mask="bytes"), 20)
+    nb = eng.make_buffers(E, None, sample=True)
+    nb.next_action.copy_(o.next_action)
+    extra["step_without_mask_per_s"] = E / timed(
+        lambda: eng.step(st, nb.next_action, buffers=nb, mask=None, sample=True, seed=11, auto_reset=True), 20)
+    del mb, st, scratch_states
     # configs[3]: batched leaf expansion feeding the torch net: obs f32 [B,8,20,20] + bool mask [B,30433] + terminal vectors
     for B in (256, 4096):
         leaves = eng.new_states(B)
@@ -357,6 +388,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mask", default="bytes", choices=["bytes", "bits"])
     ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--board", type=int, default=20, help="board size N (the headline metric is 20)")
+    ap.add_argument("--players", type=int, default=4, choices=[2, 4])
     ap.add_argument("--e2e-halves", type=int, default=2, help="half-batches pipelined on separate streams in the e2e leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the rollout / leaf-expansion extras")
