@@ -351,7 +351,7 @@ def extra_workloads(eng, torch):
         lambda: eng.step(st, nb.next_action, buffers=nb, mask=None, sample=True, seed=11, auto_reset=True), 20)
     del mb, st, scratch_states
     # configs[3]: batched leaf expansion feeding the torch net: obs f32 [B,8,20,20] + bool mask [B,30433] + terminal vectors
-    for B in (256, 4096):
+    for B in (256, 4096, 65536):
         leaves = eng.new_states(B)
         o = eng.step(leaves, None, mask=None, sample=True, seed=3)
         for _ in range(20):
@@ -359,11 +359,15 @@ def extra_workloads(eng, torch):
         buf = eng.make_buffers(B, "bytes")
         obs = torch.empty((B, 8, 20, 20), dtype=torch.float32, device=leaves.device)
 
-        def expand():
-            eng.step(leaves, None, buffers=buf, mask="bytes")
-            eng.observe(leaves, out=obs)
+        def expand():                       # one launch: legal mask + terminal vector + observation planes
+            eng.step(leaves, None, buffers=buf, mask="bytes", obs=obs)
         sec = timed(expand, 20)
         extra[f"leaf_expansions_per_s_B{B}"] = B / sec
+
+        def expand2():                      # the two-kernel form (blk_step + blk_observe), for comparison
+            eng.step(leaves, None, buffers=buf, mask="bytes")
+            eng.observe(leaves, out=obs)
+        extra[f"leaf_expansions_two_kernels_per_s_B{B}"] = B / timed(expand2, 20)
     # device-resident PUCT forest (config/mcts_blokus.yml player: MCTS with the uniform DumbNet prior), B trees in lockstep
     from blokus_rl_b200.gpu_puct import GpuPuct
     B, sims = 4096, 50

@@ -16,7 +16,7 @@ LIB_PATH = Path(_os.environ.get("BLOKUS_B200_LIB", _PKG / "libblokus_b200.so")) 
 BLK_MASK_NONE, BLK_MASK_BITS, BLK_MASK_BYTES, BLK_MASK_INDICES = 0, 1, 2, 3
 BLK_OPT_AUTO_RESET = 1
 BLK_FLAG_DONE, BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED = 1, 2, 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "blk_last_error", "blk_abi_version", "blk_create", "blk_destroy", "blk_get_info", "blk_action_to_cells",
@@ -42,6 +42,7 @@ class BlkStepArgs(C.Structure):
         ("mask", C.c_void_p), ("mask_format", C.c_int32), ("mask_stride", C.c_int64),
         ("legal_count", C.c_void_p), ("terminal", C.c_void_p), ("flags", C.c_void_p), ("scores", C.c_void_p),
         ("next_action", C.c_void_p), ("seed", C.c_uint64), ("env_id_base", C.c_uint32), ("options", C.c_uint32),
+        ("obs", C.c_void_p),
     ]
 
 

@@ -274,6 +274,7 @@ int build_tables(blk_engine *h) {
     int off = kOffWdesc + 8 * 32 * g.rounds;               // LUT at 0, gather descriptors at 2048
     t.off_obase = off;  off = align16(off + 4 * (kOrients + 1));
     t.off_wsrc = off;   off = align16(off + 2 * g.mw);
+    t.off_obslut = off; off = align16(off + 16 * 16);
     t.roll_begin = off;                                      // everything from here on is what the rollout kernel stages
     t.off_oinfo = off;  off = align16(off + 4 * (kOrients + 1));
     t.off_ocells = off; off = align16(off + 4 * (kOrients + 1));
@@ -328,6 +329,10 @@ int build_tables(blk_engine *h) {
         }
         memcpy(blob.data() + kOffLut + 8 * b, &lo, 4);
         memcpy(blob.data() + kOffLut + 8 * b + 4, &hi, 4);
+    }
+    for (int b = 0; b < 16; ++b) {
+        const float q[4] = {b & 1 ? 1.f : 0.f, b & 2 ? 1.f : 0.f, b & 4 ? 1.f : 0.f, b & 8 ? 1.f : 0.f};
+        memcpy(blob.data() + t.off_obslut + 16 * b, q, 16);
     }
     g.fld_words = (g.nf + 3 + 3) & ~3;                   // >= nf + 3 zero slots for the gather
     g.warp_smem = align16(4 * g.fld_words + 4 * 32);      // fields + 32 per-pass popcount totals (sampler)
@@ -458,6 +463,7 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
         if (args->mask_format == BLK_MASK_INDICES && (!args->legal_count || args->mask_stride < 1))
             return fail(BLK_ERR_ARG, "BLK_MASK_INDICES needs legal_count and a positive mask_stride");
     }
+    if (args->obs && (reinterpret_cast<uintptr_t>(args->obs) & 15) != 0) return fail(BLK_ERR_ARG, "obs must be 16 B aligned");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     KParams kp;
     kp.a = *args; kp.tables = h->d_tables; kp.t = h->t; kp.g = h->g;

@@ -68,6 +68,7 @@ struct TableLayout {
     int off_wsrc;    // uint16[mw]  first field intersecting mask word g
     int off_fbase;   // uint16[92]  first field index of each orientation
     int off_f2o;     // uint8[nf]   orientation of each field
+    int off_obslut;  // float4[16]  4 occupancy bits -> 4 floats (fused observation output of the step kernel)
     int bytes;       // multiple of 16
     int roll_begin;  // the rollout kernel stages only [roll_begin, bytes): oinfo, ocells, foff, fbase, f2o
     // Two tables sit at FIXED offsets so their shared-memory addresses are immediates in the unrolled emit loop:
@@ -422,6 +423,7 @@ struct SmemTables {
     const uint8_t *f2o;
     const uint2 *wdesc;
     const uint2 *lut;
+    const float4 *obslut;
 };
 __device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, const TableLayout &t, int shift = 0) {
     tab -= shift;   // `tab` holds the blob from byte `shift` on (rollout kernel): tables before it must not be touched
@@ -435,6 +437,7 @@ __device__ __forceinline__ SmemTables make_tables(const unsigned char *tab, cons
     tb.f2o = tab + t.off_f2o;
     tb.wdesc = reinterpret_cast<const uint2 *>(tab + kOffWdesc);
     tb.lut = reinterpret_cast<const uint2 *>(tab + kOffLut);
+    tb.obslut = reinterpret_cast<const float4 *>(tab + t.off_obslut);
     return tb;
 }
 
@@ -502,6 +505,47 @@ __device__ __forceinline__ float terminal_value(const EnvRegs &e, const Dims &g,
     const uint32_t win = __ballot_sync(kAllLanes, lane < g.P && my_score == best);
     const bool mine = (win >> lane) & 1u;
     return mine ? (__popc(win) == 1 ? 3.f : 1.f) : -1.f;
+}
+
+// canonical_board of the env held in `e` (blokus_wrapper.py:144-146; R13): planes 0..P-1 = occupancy of player p,
+// planes P..2P-1 = all ones for the side to move.  Lane y owns row y, so a plane is streamed by fetching the
+// row of each output element with one shuffle; at N = 20 four cells go through a 16-entry float4 LUT and every
+// warp store is 512 contiguous bytes (st.global.cs.v4), otherwise one float per lane (128 B per warp store).
+template <int kN, int kP>
+__device__ __forceinline__ void emit_observation(const EnvRegs &e, float *__restrict__ ob, const float4 *obslut,
+                                                 const Dims &g, int lane) {
+    const int N = g.N, P = g.P;
+    const int mover = static_cast<int>(e.meta & 15u);
+    if (kN == 20) {
+        float4 *o4 = reinterpret_cast<float4 *>(ob);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if (p < P) {
+                const uint32_t own = p == 0 ? e.own0 : (p == 1 ? e.own1 : (p == 2 ? e.own2 : e.own3));
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int w = it * 32 + lane;              // quad inside the plane: 100 quads of 4 cells
+                    const int y = w / 5, x0 = (w - 5 * y) * 4;
+                    const uint32_t bits = __shfl_sync(kAllLanes, own, y & 31);
+                    if (w < 100) __stcs(o4 + p * 100 + w, obslut[(bits >> x0) & 15u]);
+                }
+            }
+        }
+        const float4 ones = obslut[15], zeros = obslut[0];
+        for (int j = lane; j < P * 100; j += 32) __stcs(o4 + P * 100 + j, (j / 100 == mover) ? ones : zeros);
+    } else {
+        const int nn = N * N;
+        for (int p = 0; p < P; ++p) {
+            const uint32_t own = sel4(e.own0, e.own1, e.own2, e.own3, p);
+            for (int c0 = 0; c0 < nn; c0 += 32) {
+                const int c = c0 + lane;
+                const int y = c / N, x = c - y * N;
+                const uint32_t bits = __shfl_sync(kAllLanes, own, y & 31);
+                if (c < nn) ob[p * nn + c] = ((bits >> x) & 1u) ? 1.f : 0.f;
+            }
+        }
+        for (int j = lane; j < P * nn; j += 32) ob[P * nn + j] = (j / nn == mover) ? 1.f : 0.f;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -741,6 +785,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
         }
         if (a.flags != nullptr && lane == 0) a.flags[env] = static_cast<uint8_t>(flags);
         if (a.state_out != nullptr) env_store(e, a.state_out + env * sw, g, lane);
+        if (a.obs != nullptr) emit_observation<kN, kP>(e, a.obs + env * (2 * P * N * N), tb.obslut, g, lane);
         __syncwarp();
     }
     queue_release(kp.queue);

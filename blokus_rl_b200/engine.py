@@ -29,6 +29,7 @@ class StepOut:
     scores: torch.Tensor | None          # int16 [n, P]
     next_action: torch.Tensor | None     # int32 [n]        uniform random legal action of the new mover
     mask_raw: torch.Tensor | None = None # the padded buffer behind `mask`
+    obs: torch.Tensor | None = None      # float32 [n, 2P, N, N] observation of the resulting states (fused output)
 
 
 @dataclass
@@ -132,10 +133,13 @@ class BlokusEngine:
     def step(self, states: torch.Tensor, actions: torch.Tensor | None = None, *, out_states: torch.Tensor | None = None,
              mask: str | torch.Tensor | None = "bytes", want_count: bool = True, want_terminal: bool = True,
              want_scores: bool = True, sample: bool = False, seed: int = 0, env_id_base: int = 0,
-             auto_reset: bool = False, buffers: StepOut | None = None) -> StepOut:
+             auto_reset: bool = False, buffers: StepOut | None = None,
+             obs: torch.Tensor | bool | None = None) -> StepOut:
         """Apply ``actions`` (or none: mask-only), resolve the next mover with auto-skip, detect the end
         of the game and emit the next mover's full legal mask.  In-place on ``states`` unless
-        ``out_states`` is given (functional use, as MCTS needs: blokus_rl/alphazero/mcts.py:47)."""
+        ``out_states`` is given (functional use, as MCTS needs: blokus_rl/alphazero/mcts.py:47).  ``obs`` (a
+        float32 ``[n, 2P, N, N]`` tensor, or True to allocate one) additionally receives ``canonical_board`` of the
+        resulting states from the same kernel (blokus_wrapper.py:144-146): leaf expansion in one launch."""
         self._check_states(states)
         n = states.shape[0]
         dev = self.device
@@ -184,6 +188,16 @@ class BlokusEngine:
         flags = buf("flags", (n,), torch.uint8, True)
         scores = buf("scores", (n, P), torch.int16, want_scores)
         next_action = buf("next_action", (n,), torch.int32, sample)
+        N = self.board_size
+        if obs is True:
+            obs = getattr(b, "obs", None) if b is not None else None
+            if obs is None:
+                obs = torch.empty((n, 2 * P, N, N), dtype=torch.float32, device=dev)
+        elif obs is False:
+            obs = None
+        if obs is not None and (obs.dtype != torch.float32 or obs.device != dev or not obs.is_contiguous()
+                                or obs.numel() != n * 2 * P * N * N):
+            raise ValueError("obs must be a contiguous float32 [n, 2P, N, N] CUDA tensor")
         args = _lib.BlkStepArgs(
             n, states.data_ptr(), out_states.data_ptr(), None if actions is None else actions.data_ptr(),
             None if raw_mask is None else raw_mask.data_ptr(), fmt, stride,
@@ -191,13 +205,14 @@ class BlokusEngine:
             None if terminal is None else terminal.data_ptr(), flags.data_ptr(),
             None if scores is None else scores.data_ptr(),
             None if next_action is None else next_action.data_ptr(),
-            seed & 0xFFFFFFFFFFFFFFFF, env_id_base & 0xFFFFFFFF, BLK_OPT_AUTO_RESET if auto_reset else 0)
+            seed & 0xFFFFFFFFFFFFFFFF, env_id_base & 0xFFFFFFFF, BLK_OPT_AUTO_RESET if auto_reset else 0,
+            None if obs is None else obs.data_ptr())
         _lib.check(self._lib.blk_step(self._h, C.byref(args), self._stream()))
         view = None
         if raw_mask is not None:
             view = self.mask_view(raw_mask) if fmt == BLK_MASK_BYTES and raw_mask.shape[1] >= self.num_actions and \
                 raw_mask.dtype == torch.uint8 else raw_mask
-        return StepOut(out_states, view, legal_count, terminal, flags, scores, next_action, raw_mask)
+        return StepOut(out_states, view, legal_count, terminal, flags, scores, next_action, raw_mask, obs)
 
     def legal_mask(self, states: torch.Tensor, fmt: str = "bytes", **kw) -> StepOut:
         """valid_actions for the side to move of every state (blokus_wrapper.py:108-132)."""

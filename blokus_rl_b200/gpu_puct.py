@@ -64,6 +64,9 @@ class GpuPuct:
         # bit-packed mask gives just as well
         self.mask_fmt = "bits" if isinstance(self.evaluator, UniformEvaluator) else "bytes"
         self.buf = engine.make_buffers(self.B, self.mask_fmt)
+        # a net evaluator gets its input planes from the same launch that produces the new states and masks
+        self.obs = (torch.empty((self.B, 2 * self.P, engine.board_size, engine.board_size), dtype=torch.float32, device=dev)
+                    if getattr(self.evaluator, "wants_obs", False) else None)
         self.stage = torch.empty((self.B, engine.state_words), dtype=torch.int32, device=dev)   # blk_step output
         self.use_cuda_graph = use_cuda_graph and getattr(self.evaluator, "graph_safe", False)
         self._graphs: dict = {}         # (cpuct, epsilon_fix) -> captured simulation
@@ -105,10 +108,13 @@ class GpuPuct:
         t, B, eng = self.t, self.B, self.eng
         src = self.pool.index_select(0, t["src_slot"].long())
         out = eng.step(src, t["step_action"], out_states=self.stage, buffers=self.buf, mask=self.mask_fmt,
-                       want_count=False, want_scores=False)
+                       want_count=False, want_scores=False, obs=None if attach_only else self.obs)
         prior, pd, ps, value = None, 0, 0, None
         if not attach_only and not isinstance(self.evaluator, UniformEvaluator):
-            p, v = self.evaluator.evaluate(eng, self.stage, out.mask)
+            if self.obs is not None:
+                p, v = self.evaluator.evaluate(eng, self.stage, out.mask, obs=self.obs)
+            else:
+                p, v = self.evaluator.evaluate(eng, self.stage, out.mask)
             prior = p.contiguous()
             pd = 2 if prior.dtype == torch.float64 else 1
             if pd == 1:

@@ -28,6 +28,8 @@ import torch
 
 # ------------------------------------------------------------------------------------------------
 # evaluators:  evaluate(engine, states int32 [m, SW], mask bool [m, A]) -> (p [m, A] float, v [m, P] float)
+#   An evaluator with ``wants_obs = True`` is also handed ``obs=`` (float32 [m, 2P, N, N]) when the caller already has
+#   it from the step kernel's fused observation output (GpuPuct), and computes it itself otherwise.
 # ------------------------------------------------------------------------------------------------
 class UniformEvaluator:
     graph_safe = True          # no host work: GpuPuct may capture it into a CUDA graph
@@ -53,14 +55,15 @@ class RolloutEvaluator:
 
 class TorchNetEvaluator:
     graph_safe = True          # static-shape torch ops only
+    wants_obs = True           # blk_step can write the observation in the same launch (blk_step_args.obs)
 
     def __init__(self, model: torch.nn.Module):
         self.model = model
 
     @torch.inference_mode()
-    def evaluate(self, engine, states, mask):
+    def evaluate(self, engine, states, mask, obs=None):
         self.model.eval()
-        logits, v = self.model(engine.observe(states))
+        logits, v = self.model(engine.observe(states) if obs is None else obs)
         logits = logits.float().masked_fill(~mask, float("-inf"))
         return torch.softmax(logits, dim=-1).to(torch.float64), v.to(torch.float64)
 

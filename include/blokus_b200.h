@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BLK_ABI_VERSION 1
+#define BLK_ABI_VERSION 2
 
 typedef enum {
     BLK_OK = 0,
@@ -93,6 +93,9 @@ typedef struct {
     uint64_t seed;              /* Philox-4x32-10 key = (seed_lo, seed_hi ^ (env_id_base + i)), ctr = (ply >> 2, game, 0, 0), word ply & 3 */
     uint32_t env_id_base;       /* global id of env 0 of this batch (multi-GPU sharding keeps results partition-invariant) */
     uint32_t options;           /* BLK_OPT_* */
+    float *obs;                 /* nullable [n][2P][N][N] float32, 16 B aligned: canonical_board of the RESULTING state
+                                   (blokus_wrapper.py:144-146), written by the same kernel -- leaf expansion for the
+                                   policy/value net is then one launch: new state + legal mask + observation */
 } blk_step_args;
 
 /* Arguments of blk_rollout(): uniform-random playouts to the end of the game, one warp per game. */

@@ -42,7 +42,7 @@ class OracleEngine:
         return None
 
     def step(self, states, actions=None, *, out_states=None, mask="bytes", want_count=True, want_terminal=True,
-             want_scores=True, sample=False, seed=0, env_id_base=0, auto_reset=False, buffers=None):
+             want_scores=True, sample=False, seed=0, env_id_base=0, auto_reset=False, buffers=None, obs=None):
         orc, n, P = self.orc, states.shape[0], self.num_players
         sts = self._unpack(states)
         flags = np.zeros(n, np.uint8)
@@ -86,8 +86,14 @@ class OracleEngine:
             mt = torch.from_numpy(m.astype(bool))
             if is_t:
                 mask[:, : self.num_actions] = torch.from_numpy(m).to(mask.dtype)
+        ot = None
+        if obs is not None and obs is not False:
+            ot = torch.from_numpy(np.stack([orc.observe(s) for s in sts]))
+            if isinstance(obs, torch.Tensor):
+                obs.copy_(ot.view_as(obs))
+                ot = obs
         return StepOut(out_states, mt, torch.from_numpy(m.sum(1).astype(np.int32)), torch.from_numpy(term),
-                       torch.from_numpy(flags), torch.from_numpy(scores), nxt, None)
+                       torch.from_numpy(flags), torch.from_numpy(scores), nxt, None, ot)
 
     def legal_mask(self, states, fmt="bytes", **kw):
         return self.step(states, None, mask=fmt, **kw)

@@ -138,6 +138,46 @@ def test_observation_and_board_contents(engine20, oracle20, engine7, oracle7):
             assert (term[i].cpu().numpy() == orc.terminal_values(o)).all()
 
 
+def test_fused_observation_output(engine20, oracle20, engine7, oracle7):
+    """blk_step_args.obs: the step kernel writes canonical_board of the RESULTING state (after the move, the
+    next-mover resolution and a possible auto-reset) -- equal to the oracle's observation of the oracle's next
+    state and to the stand-alone blk_observe, for every kernel variant (mask formats, sampler, geometries)."""
+    import torch
+    from blokus_rl_b200 import BlokusEngine
+    from oracle.oracle import Oracle
+    extra = [(BlokusEngine(n, p), Oracle(n, p)) for n, p in ((20, 2), (14, 4), (9, 4))]
+    for eng, orc in [(engine20, oracle20), (engine7, oracle7)] + extra:
+        n, seed, P, N = 37, 21, eng.num_players, eng.board_size
+        s = eng.new_states(n)
+        ost = [orc.new_state() for _ in range(n)]
+        out = eng.step(s, None, mask="bits", sample=True, seed=seed, obs=True)
+        torch.cuda.synchronize()
+        assert out.obs.shape == (n, 2 * P, N, N)
+        assert (out.obs.cpu().numpy() == np.stack([orc.observe(o) for o in ost])).all()
+        fmts = ["bytes", "bits", None, "indices"]
+        for ply in range(40 if N == 20 else 14):
+            acts = out.next_action.clone()
+            obs_buf = torch.full((n, 2 * P, N, N), 7.0, device=s.device)
+            out = eng.step(s, acts, mask=fmts[ply % 4], sample=True, seed=seed, auto_reset=True, obs=obs_buf)
+            torch.cuda.synchronize()
+            assert out.obs is obs_buf
+            a = acts.cpu().numpy()
+            for i, o in enumerate(ost):
+                assert orc.step(o, int(a[i])) == 0
+                if orc.field(o, "done"):
+                    orc.reset(o, orc.field(o, "game") + 1)
+            want = np.stack([orc.observe(o) for o in ost])
+            assert (obs_buf.cpu().numpy() == want).all(), (N, P, ply)
+            assert (eng.observe(s).cpu().numpy() == want).all()
+        # functional form without the sampler (the PUCT forest's call): obs belongs to out_states, not to the inputs
+        dst = torch.empty_like(s)
+        o2 = eng.step(s, out.next_action, out_states=dst, mask="bytes", obs=True)
+        torch.cuda.synchronize()
+        assert (o2.obs == eng.observe(dst)).all() and not (o2.obs == eng.observe(s)).all()
+    with pytest.raises(ValueError):
+        engine20.step(engine20.new_states(2), None, obs=torch.empty((2, 8, 20, 19), device="cuda"))
+
+
 def test_unaligned_and_contiguous_bool_mask(engine20, oracle20, engine7):
     """Caller-provided contiguous bool [n, A] buffers (row stride 30,433: every row starts at a different offset inside
     a 16 B chunk) and arbitrarily offset bases give the same masks as the padded layout, and neighbours stay intact."""
