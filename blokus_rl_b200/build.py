@@ -17,8 +17,10 @@ CSRC = PKG / "csrc"
 OBJ = PKG / "build"
 OUT = PKG / "libblokus_b200.so"
 DEPS = [CSRC / "blk_engine.cu", CSRC / "blk_inst.cu", CSRC / "blk_puct.cu", CSRC / "blk_kernels.cuh", CSRC / "blk_orient.inc",
+        CSRC / "blk_small.cu", CSRC / "blk_small_fields.inc",
         ROOT / "include" / "blokus_b200.h"]
 GEOMETRIES = [(20, 4), (20, 2), (14, 4), (14, 2), (7, 2), (0, 0)]
+SMALL_SIZES = [5, 6, 7]          # thread-per-env kernels on 64-bit bitboards (csrc/blk_small.cu)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -32,6 +34,9 @@ def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | N
     for n, p in GEOMETRIES:
         jobs.append((OBJ / f"blk_inst_{n}_{p}.o",
                      ["nvcc", *flags, f"-DBLK_INST_N={n}", f"-DBLK_INST_P={p}", "-c", str(CSRC / "blk_inst.cu")]))
+
+    for n in SMALL_SIZES:
+        jobs.append((OBJ / f"blk_small_{n}.o", ["nvcc", *flags, f"-DBLK_SMALL_N={n}", "-c", str(CSRC / "blk_small.cu")]))
 
     def run(job):
         obj, cmd = job

@@ -221,6 +221,10 @@ struct blk_engine {
     int step_blocks_per_sm = 0, rollout_blocks_per_sm = 0;
     bool special = false;
     KernelSet ks = {};                               // step[mask format variant][sampler], rollout
+    bool small = false;                              // N <= 7: thread-per-env kernels (blk_small.cu) for the common formats
+    SmallKernelSet sks = {};
+    unsigned char *d_small = nullptr;                // ocells64[92] | first_mask[mw]
+    int first_count = 0, small_blocks_per_sm = 0;
     std::vector<int32_t> obase;        // host copies for blk_action_to_cells
     std::vector<int16_t> act_o, act_y, act_x;
 };
@@ -403,6 +407,36 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_blocks_per_sm, h->ks.step[2][1], kWarps * 32, h->step_smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, h->ks.rollout, kRollWarps * 32, h->roll_smem);
     if (h->step_blocks_per_sm < 1 || h->rollout_blocks_per_sm < 1) { blk_destroy(h); return fail(BLK_ERR_CUDA, "kernel does not fit on an SM"); }
+    if (N <= 7) {
+        h->sks = N == 5 ? kernels_small_5() : (N == 6 ? kernels_small_6() : kernels_small_7());
+        if (h->sks.num_actions != h->g.A) { blk_destroy(h); return fail(BLK_ERR_ARG, "internal: small-board tables are stale"); }
+        // footprints with row stride 8, and the (constant) legal mask of the fresh board: every footprint that
+        // covers player 0's start corner (0, 0)
+        std::vector<unsigned char> blob(8 * 92 + 4 * h->g.mw, 0);
+        uint64_t *oc = reinterpret_cast<uint64_t *>(blob.data());
+        uint32_t *fm = reinterpret_cast<uint32_t *>(blob.data() + 8 * 92);
+        for (int o = 0; o < kOrients; ++o)
+            for (int c = 0; c < kOrient[o].n; ++c) oc[o] |= 1ull << (8 * kOrient[o].yx[2 * c] + kOrient[o].yx[2 * c + 1]);
+        for (int act = 0; act < h->g.A; ++act) {
+            if (h->act_y[act] != 0 || h->act_x[act] != 0) continue;
+            const OrientRow &r = kOrient[h->act_o[act]];
+            bool corner = false;
+            for (int c = 0; c < r.n; ++c) corner |= r.yx[2 * c] == 0 && r.yx[2 * c + 1] == 0;
+            if (corner) { fm[act >> 5] |= 1u << (act & 31); ++h->first_count; }
+        }
+        if (cudaMalloc(&h->d_small, blob.size()) != cudaSuccess ||
+            cudaMemcpy(h->d_small, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            blk_destroy(h); return fail(BLK_ERR_CUDA, "small-board table upload failed");
+        }
+        const int pi = P == 4 ? 1 : 0;
+        for (int f = 0; f < 3; ++f)
+            for (int sm = 0; sm < 2; ++sm)
+                if (cudaFuncSetAttribute(h->sks.step[pi][f][sm], cudaFuncAttributeMaxDynamicSharedMemorySize, h->sks.smem[pi]) != cudaSuccess) {
+                    blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed for the small-board kernels");
+                }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->small_blocks_per_sm, h->sks.step[pi][2][1], h->sks.threads[pi], h->sks.smem[pi]);
+        h->small = h->small_blocks_per_sm >= 1;
+    }
     *out = h;
     return BLK_OK;
 }
@@ -411,6 +445,7 @@ void blk_destroy(blk_engine *h) {
     if (!h) return;
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_queue) cudaFree(h->d_queue);
+    if (h->d_small) cudaFree(h->d_small);
     delete h;
 }
 
@@ -474,6 +509,19 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
     if (variant == BLK_MASK_BYTES &&
         ((args->mask_stride & 15) != 0 || (reinterpret_cast<uintptr_t>(args->mask) & 15) != 0 || args->mask_stride < h->g.mask_bytes))
         variant = 3;
+    if (h->small && variant <= 2 && !args->obs) {
+        // N <= 7: one env per thread on 64-bit bitboards (blk_small.cu); the other formats stay on the warp-per-env kernel
+        SmallParams sp;
+        sp.a = *args; sp.tables = h->d_tables; sp.t = h->t; sp.g = h->g;
+        sp.ocells64 = reinterpret_cast<const uint64_t *>(h->d_small);
+        sp.first_mask = reinterpret_cast<const uint32_t *>(h->d_small + 8 * 92);
+        sp.first_count = h->first_count;
+        const int pi = h->g.P == 4 ? 1 : 0;
+        const int sgrid = grid_for(args->n, h->sks.threads[pi], h->sm_count, h->small_blocks_per_sm);
+        h->sks.step[pi][variant][args->next_action != nullptr ? 1 : 0]<<<sgrid, h->sks.threads[pi], h->sks.smem[pi], static_cast<cudaStream_t>(stream)>>>(sp);
+        CUDA_TRY(cudaGetLastError());
+        return BLK_OK;
+    }
     h->ks.step[variant][args->next_action != nullptr ? 1 : 0]<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(kp);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;

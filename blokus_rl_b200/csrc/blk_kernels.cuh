@@ -950,6 +950,25 @@ inline KernelSet make_kernel_set() {
     k.rollout = rollout_kernel<kN, kP>;
     return k;
 }
+// Small boards (N <= 7): thread-per-env kernels on 64-bit bitboards, one translation unit per N (blk_small.cu)
+struct SmallParams {
+    blk_step_args a;
+    const unsigned char *tables;
+    TableLayout t;
+    Geometry g;
+    const uint64_t *ocells64;     // [92] footprint of each orientation, row stride 8
+    const uint32_t *first_mask;   // legal mask words of the fresh board (player 0's first move)
+    int first_count;
+};
+using SmallStepFn = void (*)(const SmallParams);
+struct SmallKernelSet {
+    SmallStepFn step[2][3][2];    // [P == 4][mask format: none, bits, bytes (aligned rows)][sampler]
+    int smem[2], threads[2];
+    int num_actions;
+};
+SmallKernelSet kernels_small_5();
+SmallKernelSet kernels_small_6();
+SmallKernelSet kernels_small_7();
 KernelSet kernels_20_4();   // the headline geometry: every address and trip count is a compile-time constant
 KernelSet kernels_20_2();
 KernelSet kernels_14_4();
