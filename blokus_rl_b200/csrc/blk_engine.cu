@@ -509,7 +509,9 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
     if (variant == BLK_MASK_BYTES &&
         ((args->mask_stride & 15) != 0 || (reinterpret_cast<uintptr_t>(args->mask) & 15) != 0 || args->mask_stride < h->g.mask_bytes))
         variant = 3;
-    if (h->small && variant <= 2 && !args->obs) {
+    const bool bits_rows_8b = variant != BLK_MASK_BITS ||
+                              ((args->mask_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(args->mask) & 7) == 0);
+    if (h->small && variant <= 2 && !args->obs && bits_rows_8b) {
         // N <= 7: one env per thread on 64-bit bitboards (blk_small.cu); the other formats stay on the warp-per-env kernel
         SmallParams sp;
         sp.a = *args; sp.tables = h->d_tables; sp.t = h->t; sp.g = h->g;

@@ -46,7 +46,7 @@ constexpr uint64_t small_full() {
 constexpr uint64_t kSFull = small_full();
 
 // control word of a slot between rounds
-constexpr uint32_t kCtlMoved = 1u << 8, kCtlEnded = 1u << 11, kCtlIllegal = 1u << 12,
+constexpr uint32_t kCtlFresh = 1u << 9, kCtlMoved = 1u << 8, kCtlEnded = 1u << 11, kCtlIllegal = 1u << 12,
                    kCtlWasDone = 1u << 13;
 
 __device__ __forceinline__ uint64_t rows_to_board(const uint32_t *rows) {
@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, 2) small_step_kernel(co
     uint32_t *s_oinfo = reinterpret_cast<uint32_t *>(s_obase + 92);       // [92]
     uint64_t *s_ocells = reinterpret_cast<uint64_t *>(s_oinfo + 92);      // [92] footprints, row stride 8
     uint32_t *s_first = reinterpret_cast<uint32_t *>(s_ocells + 92);      // [kSMW] mask of the fresh board
+    uint16_t *s_fck = reinterpret_cast<uint16_t *>(s_first + kSMW);       // [4] its cumulative counts per 16 words
 
     const blk_step_args &a = sp.a;
     const int tid = threadIdx.x;
@@ -166,6 +167,13 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, 2) small_step_kernel(co
         s_ocells[i] = i < kOrients ? sp.ocells64[i] : 0ull;
     }
     for (int i = tid; i < kSMW; i += T) s_first[i] = sp.first_mask[i];
+    if (tid == 0) {
+        int run = 0;
+        for (int k = 0; k < kSMW; ++k) {
+            run += __popc(sp.first_mask[k]);
+            if ((k & 15) == 15 && k / 16 < kSCk) s_fck[k / 16] = static_cast<uint16_t>(run);
+        }
+    }
 
     const int64_t n = a.n;
     for (int64_t base = static_cast<int64_t>(blockIdx.x) * T; base < n; base += static_cast<int64_t>(gridDim.x) * T) {
@@ -287,14 +295,8 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, 2) small_step_kernel(co
 #pragma unroll
                         for (int q = 0; q < P; ++q) s2[P * N + q] = kFullInv;
                         s2[kMeta] = 0u; s2[kMeta + 1] = game; s2[kMeta + 2] = 0u; s2[kMeta + 3] = 0u;
-                        int run = 0;
-                        for (int k = 0; k < kSMW; ++k) {                       // a fresh board's mask is a constant
-                            const uint32_t v = s_first[k];
-                            r2[k] = v;
-                            run += __popc(v);
-                            if ((k & 15) == 15 && k / 16 < kSCk) s_ck[4 * slot + k / 16] = static_cast<uint16_t>(run);
-                        }
-                        s_cnt[slot] = sp.first_count;
+                        ctl |= kCtlFresh;                          // a fresh board's mask is a constant: the sampler and the
+                        s_cnt[slot] = sp.first_count;               // write-back read s_first instead of this slot's row
                     } else {
                         s2[kMeta] |= 1u << 4;                      // done; the mover stays the last mover
                     }
@@ -315,6 +317,8 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, 2) small_step_kernel(co
             const uint32_t ctl = s_ctl[tid];
             const int cnt = s_cnt[tid];
             const bool ended = (ctl & kCtlEnded) != 0u;
+            const uint32_t *mrow = (ctl & kCtlFresh) ? s_first : row;
+            const uint16_t *mck = (ctl & kCtlFresh) ? s_fck : s_ck + 4 * tid;
             if (a.legal_count != nullptr) a.legal_count[env] = cnt;
             if (kSample) {
                 int pick = -1;
@@ -327,15 +331,15 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, 2) small_step_kernel(co
                     int w = 0;
 #pragma unroll
                     for (int j = kSCk - 1; j >= 0; --j) {                      // first level: which run of 16 words
-                        const int cj = s_ck[4 * tid + j];
+                        const int cj = mck[j];
                         if (w == 0 && k >= cj) { w = 16 * (j + 1); k -= cj; }
                     }
-                    uint32_t word = row[w];
+                    uint32_t word = mrow[w];
                     for (;;) {
                         const int c = __popc(word);
                         if (k < c) break;
                         k -= c;
-                        word = row[++w];
+                        word = mrow[++w];
                     }
                     pick = (w << 5) + kth_set_bit(word, k);
                 }
@@ -368,17 +372,18 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, 2) small_step_kernel(co
         if (kFmt == 1) {
             constexpr int kMwPad = ((kSA + 31) / 32 + 3) & ~3;      // Geometry::mw
             for (int slot = warp; slot < m; slot += T / 32) {
-                uint32_t *out = reinterpret_cast<uint32_t *>(a.mask) + (base + slot) * a.mask_stride;
-                const uint32_t *r = s_mask + slot * kSRS;
+                uint2 *out = reinterpret_cast<uint2 *>(reinterpret_cast<uint32_t *>(a.mask) + (base + slot) * a.mask_stride);
+                const uint32_t *r = (s_ctl[slot] & kCtlFresh) ? s_first : s_mask + slot * kSRS;
 #pragma unroll
-                for (int w = lane; w < kMwPad; w += 32) out[w] = w < kSMW ? r[w] : 0u;
+                for (int w = lane; w < kMwPad / 2; w += 32)          // rows are 16 B aligned (mask_words is a multiple of 4)
+                    out[w] = make_uint2(2 * w < kSMW ? r[2 * w] : 0u, 2 * w + 1 < kSMW ? r[2 * w + 1] : 0u);
             }
         } else if (kFmt == 2) {
             constexpr int kChunks = (kSA + BLK_ROW_ALIGN - 1) / BLK_ROW_ALIGN * BLK_ROW_ALIGN / 16;   // Geometry::mask_bytes / 16
             const unsigned char *lutb = reinterpret_cast<const unsigned char *>(s_lut);
             for (int slot = warp; slot < m; slot += T / 32) {
                 unsigned char *out = reinterpret_cast<unsigned char *>(a.mask) + (base + slot) * a.mask_stride;
-                const uint32_t *r = s_mask + slot * kSRS;
+                const uint32_t *r = (s_ctl[slot] & kCtlFresh) ? s_first : s_mask + slot * kSRS;
 #pragma unroll
                 for (int c = lane; c < kChunks; c += 32) {
                     const int w = c >> 1;
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, 2) small_step_kernel(co
 static int small_smem_bytes(int P) {
     const int T = P == 2 ? kST2 : kST4;
     const int SWP = (P * kSN + P + 4) | 1;
-    return 4 * T * kSRS + 4 * T * SWP + 4 * T + 4 * T + 8 * T + 8 * T + 4 * T + 16 + 2048 + 4 * 92 + 4 * 92 + 8 * 92 + 4 * kSMW + 16;
+    return 4 * T * kSRS + 4 * T * SWP + 4 * T + 4 * T + 8 * T + 8 * T + 4 * T + 16 + 2048 + 4 * 92 + 4 * 92 + 8 * 92 + 4 * kSMW + 8 + 16;
 }
 
 #define BLK_SCAT_(n) kernels_small_##n
