@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""Random-play step throughput for other board sizes / player counts (runtime-dimension kernels)."""
+"""Random-play step throughput for every board size / player count with its own kernels: thread-per-env kernels
+for N <= 7 (csrc/blk_small.cu), warp-per-env specialisations for 14x14 and 20x20."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
 from blokus_rl_b200 import BlokusEngine
-for (N, P, n) in ((7, 2, 262144), (14, 2, 131072), (14, 4, 131072), (20, 2, 65536), (20, 4, 65536)):
+for (N, P, n) in ((5, 2, 1048576), (6, 2, 1048576), (7, 2, 1048576), (7, 4, 1048576), (14, 2, 131072), (14, 4, 131072),
+                  (20, 2, 65536), (20, 4, 65536)):
     eng = BlokusEngine(N, P)
     for fmt in ("bytes", "bits"):
         s = eng.new_states(n)
