@@ -13,7 +13,7 @@ from helpers import lockstep
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 total_steps = total_games = 0
 t0 = time.time()
-for (N, P, rule, n, plies, seed) in ((20, 4, 0, 1500, 200, 11), (20, 4, 1, 600, 150, 12), (20, 2, 0, 400, 120, 13),
+for (N, P, rule, n, plies, seed) in ((7, 2, 1, 800, 100, 21), (6, 4, 0, 400, 80, 22), (5, 4, 1, 400, 60, 23), (6, 2, 1, 400, 80, 24), (20, 4, 0, 1500, 200, 11), (20, 4, 1, 600, 150, 12), (20, 2, 0, 400, 120, 13),
                                      (14, 2, 1, 800, 150, 14), (14, 4, 0, 500, 150, 15), (7, 2, 0, 1500, 120, 16),
                                      (7, 4, 0, 400, 100, 17), (10, 2, 1, 400, 120, 18), (5, 2, 0, 400, 60, 19)):
     eng, orc = BlokusEngine(N, P, score_rule=rule), Oracle(N, P, rule)
