@@ -350,6 +350,35 @@ def extra_workloads(eng, torch):
     extra["step_without_mask_per_s"] = E / timed(
         lambda: eng.step(st, nb.next_action, buffers=nb, mask=None, sample=True, seed=11, auto_reset=True), 20)
     del mb, st, scratch_states
+    # Everything through HOST buffers (states, actions in; states, masks, outputs back), for the record: this is what
+    # a caller pays who keeps nothing on the device.  PCIe carries 30 KB of byte mask (or 3.8 KB of bit mask) per env
+    # and step, so the link, not the kernel, sets the rate -- which is why the adapters keep states and masks on the GPU.
+    for fmt in ("bytes", "bits"):
+        E = 8192
+        d_st = eng.new_states(E)
+        o = eng.step(d_st, None, mask=None, sample=True, seed=13)
+        for _ in range(16):
+            o = eng.step(d_st, o.next_action, mask=None, sample=True, seed=13)
+        hb = eng.make_buffers(E, fmt, sample=True)
+        h_st = d_st.cpu().pin_memory()
+        h_act = o.next_action.cpu().pin_memory()
+        h_mask = torch.empty(hb.mask_raw.shape, dtype=hb.mask_raw.dtype).pin_memory()
+        h_flags = torch.empty(E, dtype=torch.uint8).pin_memory()
+        h_term = torch.empty((E, 4), dtype=torch.float32).pin_memory()
+        d_act = torch.empty(E, dtype=torch.int32, device=d_st.device)
+
+        def host_step():
+            d_st.copy_(h_st, non_blocking=True)
+            d_act.copy_(h_act, non_blocking=True)
+            r = eng.step(d_st, d_act, buffers=hb, mask=fmt, sample=True, seed=13, auto_reset=True)
+            h_st.copy_(d_st, non_blocking=True)
+            h_mask.copy_(r.mask_raw, non_blocking=True)
+            h_act.copy_(r.next_action, non_blocking=True)
+            h_flags.copy_(r.flags, non_blocking=True)
+            h_term.copy_(r.terminal, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        extra[f"e2e_all_host_buffers_{fmt}_per_s"] = E / timed(host_step, 10)
+        del hb, h_mask
     # configs[3]: batched leaf expansion feeding the torch net: obs f32 [B,8,20,20] + bool mask [B,30433] + terminal vectors
     for B in (256, 4096, 65536):
         leaves = eng.new_states(B)
