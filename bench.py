@@ -397,6 +397,18 @@ def extra_workloads(eng, torch):
             eng.step(leaves, None, buffers=buf, mask="bytes")
             eng.observe(leaves, out=obs)
         extra[f"leaf_expansions_two_kernels_per_s_B{B}"] = B / timed(expand2, 20)
+    # the reference's "simplified Blokus" (config/ppo_blokus_7x7.yml): 7x7, two players, thread-per-env kernels
+    from blokus_rl_b200 import BlokusEngine
+    e7 = BlokusEngine(7, 2, device=eng.device)
+    for fmt in ("bytes", "bits"):
+        E = 1 << 20
+        st = e7.new_states(E)
+        b7 = e7.make_buffers(E, fmt, sample=True)
+        e7.step(st, None, buffers=b7, mask=fmt, sample=True, seed=1)
+        sec = timed(lambda: e7.step(st, b7.next_action, buffers=b7, mask=fmt, sample=True, seed=1, auto_reset=True), 30)
+        extra[f"steps_per_s_7x7_2p_{fmt}_1M_envs"] = E / sec
+        del st, b7
+    e7.close()
     # device-resident PUCT forest (config/mcts_blokus.yml player: MCTS with the uniform DumbNet prior), B trees in lockstep
     from blokus_rl_b200.gpu_puct import GpuPuct
     B, sims = 4096, 50
