@@ -15,6 +15,7 @@ LIB_PATH = Path(_os.environ.get("BLOKUS_B200_LIB", _PKG / "libblokus_b200.so")) 
 
 BLK_MASK_NONE, BLK_MASK_BITS, BLK_MASK_BYTES, BLK_MASK_INDICES = 0, 1, 2, 3
 BLK_OPT_AUTO_RESET = 1
+BLK_OPT_WARP_KERNELS = 2
 BLK_FLAG_DONE, BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED = 1, 2, 4
 ABI_VERSION = 2
 

@@ -511,7 +511,7 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
         variant = 3;
     const bool bits_rows_8b = variant != BLK_MASK_BITS ||
                               ((args->mask_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(args->mask) & 7) == 0);
-    if (h->small && variant <= 2 && !args->obs && bits_rows_8b) {
+    if (h->small && variant <= 2 && bits_rows_8b && !(args->options & BLK_OPT_WARP_KERNELS)) {
         // N <= 7: one env per thread on 64-bit bitboards (blk_small.cu); the other formats stay on the warp-per-env kernel
         SmallParams sp;
         sp.a = *args; sp.tables = h->d_tables; sp.t = h->t; sp.g = h->g;

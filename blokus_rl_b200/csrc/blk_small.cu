@@ -6,7 +6,7 @@
 // row 7 are zero padding, so shifted reads never wrap into a neighbouring row), which makes an orientation's
 // legality at ALL anchors a chain of 64-bit ANDs / ORs over shifted copies of the "free" and "diagonal contact"
 // boards -- 32 envs per warp instruction instead of one env per warp with 7 of 32 lanes busy (the warp-per-env
-// kernel in blk_kernels.cuh, which stays the path for N >= 8, unaligned byte masks, index lists and fused obs).
+// kernel in blk_kernels.cuh, which stays the path for N >= 8, unaligned byte masks and index lists).
 // The action-id-ordered mask words are assembled in registers by straight-line code whose bit positions are all
 // compile-time constants (blk_small_fields.inc, generated) and parked in shared memory; the block then streams
 // states and masks to HBM cooperatively (coalesced 16 B stores through the same byte LUT as the big kernel).
@@ -369,6 +369,21 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, kP == 2 ? 2 : 3) small_
             }
         // one warp per env row, lanes across the row: no index divisions, 128 B (bits) / 512 B (bytes) per warp store
         const int warp = tid >> 5, lane = tid & 31;
+        if (a.obs != nullptr) {
+            // canonical_board of the resulting state (R13): planes 0..P-1 occupancy, planes P..2P-1 one-hot mover
+            constexpr int NN = N * N, kObs = 2 * P * NN;
+            for (int slot = warp; slot < m; slot += T / 32) {
+                const uint32_t *s2 = s_state + slot * SWP;
+                float *ob = a.obs + (base + slot) * kObs;
+                const int mover = s2[kMeta] & 15u;
+#pragma unroll 4
+                for (int j = lane; j < kObs; j += 32) {
+                    const int plane = j / NN, c = j - plane * NN, y = c / N, x = c - y * N;
+                    const bool on = plane < P ? ((s2[plane * N + y] >> x) & 1u) != 0u : (plane - P == mover);
+                    ob[j] = on ? 1.f : 0.f;
+                }
+            }
+        }
         if (kFmt == 1) {
             constexpr int kMwPad = ((kSA + 31) / 32 + 3) & ~3;      // Geometry::mw
             for (int slot = warp; slot < m; slot += T / 32) {

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (BLK_FLAG_DONE, BLK_FLAG_ILLEGAL, BLK_MASK_BITS, BLK_MASK_BYTES, BLK_MASK_INDICES, BLK_MASK_NONE,
-                   BLK_OPT_AUTO_RESET, EngineError)
+                   BLK_OPT_AUTO_RESET, BLK_OPT_WARP_KERNELS, EngineError)
 
 __all__ = ["BlokusEngine", "StepOut", "RolloutOut", "EngineError", "BLK_FLAG_DONE", "BLK_FLAG_ILLEGAL"]
 
@@ -134,12 +134,14 @@ class BlokusEngine:
              mask: str | torch.Tensor | None = "bytes", want_count: bool = True, want_terminal: bool = True,
              want_scores: bool = True, sample: bool = False, seed: int = 0, env_id_base: int = 0,
              auto_reset: bool = False, buffers: StepOut | None = None,
-             obs: torch.Tensor | bool | None = None) -> StepOut:
+             obs: torch.Tensor | bool | None = None, warp_kernels: bool = False) -> StepOut:
         """Apply ``actions`` (or none: mask-only), resolve the next mover with auto-skip, detect the end
         of the game and emit the next mover's full legal mask.  In-place on ``states`` unless
         ``out_states`` is given (functional use, as MCTS needs: blokus_rl/alphazero/mcts.py:47).  ``obs`` (a
         float32 ``[n, 2P, N, N]`` tensor, or True to allocate one) additionally receives ``canonical_board`` of the
-        resulting states from the same kernel (blokus_wrapper.py:144-146): leaf expansion in one launch."""
+        resulting states from the same kernel (blokus_wrapper.py:144-146): leaf expansion in one launch.
+        ``warp_kernels`` selects the warp-per-env kernels on boards that also have thread-per-env kernels (N <= 7):
+        same results, for cross-checks."""
         self._check_states(states)
         n = states.shape[0]
         dev = self.device
@@ -205,7 +207,7 @@ class BlokusEngine:
             None if terminal is None else terminal.data_ptr(), flags.data_ptr(),
             None if scores is None else scores.data_ptr(),
             None if next_action is None else next_action.data_ptr(),
-            seed & 0xFFFFFFFFFFFFFFFF, env_id_base & 0xFFFFFFFF, BLK_OPT_AUTO_RESET if auto_reset else 0,
+            seed & 0xFFFFFFFFFFFFFFFF, env_id_base & 0xFFFFFFFF, (BLK_OPT_AUTO_RESET if auto_reset else 0) | (BLK_OPT_WARP_KERNELS if warp_kernels else 0),
             None if obs is None else obs.data_ptr())
         _lib.check(self._lib.blk_step(self._h, C.byref(args), self._stream()))
         view = None

@@ -70,7 +70,9 @@ typedef struct {
 
 typedef struct blk_engine blk_engine;
 
-enum { BLK_OPT_AUTO_RESET = 1 };
+/* BLK_OPT_WARP_KERNELS: use the warp-per-env kernels even where a board size has thread-per-env kernels (N <= 7);
+ * same results, slower -- kept for cross-checking the two implementations against each other. */
+enum { BLK_OPT_AUTO_RESET = 1, BLK_OPT_WARP_KERNELS = 2 };
 #define BLK_ACTION_NONE (-1)   /* per-env "do not move": the env only gets its mask / status refreshed */
 enum { BLK_FLAG_DONE = 1, BLK_FLAG_ILLEGAL = 2, BLK_FLAG_TRUNCATED = 4 };
 

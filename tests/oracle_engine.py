@@ -42,7 +42,7 @@ class OracleEngine:
         return None
 
     def step(self, states, actions=None, *, out_states=None, mask="bytes", want_count=True, want_terminal=True,
-             want_scores=True, sample=False, seed=0, env_id_base=0, auto_reset=False, buffers=None, obs=None):
+             want_scores=True, sample=False, seed=0, env_id_base=0, auto_reset=False, buffers=None, obs=None, warp_kernels=False):
         orc, n, P = self.orc, states.shape[0], self.num_players
         sts = self._unpack(states)
         flags = np.zeros(n, np.uint8)

@@ -1,6 +1,6 @@
 """Boards up to 7x7 run on the thread-per-env kernels (csrc/blk_small.cu).  They are checked against the oracle move by
 move (every (N, P) they are instantiated for, with and without auto-reset) and, at full batch size, against the
-warp-per-env kernels, which the engine still uses for these boards whenever the fused observation is requested."""
+warp-per-env kernels, which stay selectable for these boards (BLK_OPT_WARP_KERNELS)."""
 import numpy as np
 import pytest
 
@@ -59,22 +59,24 @@ def test_illegal_actions_small(engine7, oracle7):
 
 
 def test_small_kernels_equal_warp_kernels_at_full_batch(engine7):
-    """65,536 envs of random play: the thread-per-env kernels and the warp-per-env kernels (selected by asking for the
-    fused observation) agree bit for bit on states, masks, counts, sampled actions, flags, terminal vectors, scores."""
+    """65,536 envs of random play: the thread-per-env kernels and the warp-per-env kernels (BLK_OPT_WARP_KERNELS) agree
+    bit for bit on states, masks, counts, sampled actions, flags, terminal vectors, scores and observation planes."""
     import torch
     eng = engine7
     n, seed = 65536, 0xABCDEF
     a = eng.new_states(n)
     b = a.clone()
     oa = eng.step(a, None, mask="bits", sample=True, seed=seed)
-    ob = eng.step(b, None, mask="bits", sample=True, seed=seed, obs=True)
+    ob = eng.step(b, None, mask="bits", sample=True, seed=seed, warp_kernels=True)
     checked = 0
     for ply in range(30):
         fmt = "bytes" if ply % 2 else "bits"
         act = oa.next_action.clone()
         assert (oa.next_action == ob.next_action).all()
-        oa = eng.step(a, act, mask=fmt, sample=True, seed=seed, auto_reset=True)
-        ob = eng.step(b, act, mask=fmt, sample=True, seed=seed, auto_reset=True, obs=True)
+        oa = eng.step(a, act, mask=fmt, sample=True, seed=seed, auto_reset=True, obs=ply % 5 == 0)
+        ob = eng.step(b, act, mask=fmt, sample=True, seed=seed, auto_reset=True, obs=ply % 5 == 0, warp_kernels=True)
+        if ply % 5 == 0:
+            assert (oa.obs == ob.obs).all() and (oa.obs == eng.observe(a)).all(), f"observations differ at ply {ply}"
         assert (a == b).all(), f"states differ at ply {ply}"
         assert (oa.mask == ob.mask).all(), f"masks differ at ply {ply}"
         for name in ("legal_count", "flags", "terminal", "scores", "next_action"):
