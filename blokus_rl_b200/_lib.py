@@ -52,7 +52,7 @@ class BlkRolloutArgs(C.Structure):
         ("n_roots", C.c_int64), ("roots", C.c_void_p), ("per_root", C.c_int32), ("seed", C.c_uint64),
         ("rollout_id_base", C.c_uint32), ("final_scores", C.c_void_p), ("winners", C.c_void_p),
         ("value_sum", C.c_void_p), ("action_log", C.c_void_p), ("log_stride", C.c_int32), ("plies", C.c_void_p),
-        ("stop_player", C.c_int32), ("state_out", C.c_void_p),
+        ("stop_player", C.c_int32), ("state_out", C.c_void_p), ("options", C.c_uint32),
     ]
 
 

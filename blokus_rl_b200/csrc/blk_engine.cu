@@ -224,7 +224,7 @@ struct blk_engine {
     bool small = false;                              // N <= 7: thread-per-env kernels (blk_small.cu) for the common formats
     SmallKernelSet sks = {};
     unsigned char *d_small = nullptr;                // ocells64[92] | first_mask[mw]
-    int first_count = 0, small_blocks_per_sm = 0;
+    int first_count = 0, small_blocks_per_sm = 0, small_roll_blocks_per_sm = 0;
     std::vector<int32_t> obase;        // host copies for blk_action_to_cells
     std::vector<int16_t> act_o, act_y, act_x;
 };
@@ -434,8 +434,12 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
                 if (cudaFuncSetAttribute(h->sks.step[pi][f][sm], cudaFuncAttributeMaxDynamicSharedMemorySize, h->sks.smem[pi]) != cudaSuccess) {
                     blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed for the small-board kernels");
                 }
+        if (cudaFuncSetAttribute(h->sks.rollout[pi], cudaFuncAttributeMaxDynamicSharedMemorySize, h->sks.roll_smem) != cudaSuccess) {
+            blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed for the small-board playout kernel");
+        }
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->small_blocks_per_sm, h->sks.step[pi][2][1], h->sks.threads[pi], h->sks.smem[pi]);
-        h->small = h->small_blocks_per_sm >= 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->small_roll_blocks_per_sm, h->sks.rollout[pi], h->sks.roll_threads, h->sks.roll_smem);
+        h->small = h->small_blocks_per_sm >= 1 && h->small_roll_blocks_per_sm >= 1;
     }
     *out = h;
     return BLK_OK;
@@ -584,6 +588,17 @@ int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream) {
     if (args->stop_player < -1 || args->stop_player >= h->g.P) return fail(BLK_ERR_ARG, "stop_player out of range");
     if (args->action_log && args->log_stride < 4 * kPieces + 1) return fail(BLK_ERR_ARG, "log_stride must be >= 85");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->small && !(args->options & BLK_OPT_WARP_KERNELS)) {
+        // N <= 7: one playout per thread on 64-bit bitboards (blk_small.cu); identical games, ~an order of magnitude faster
+        SmallRollParams sp;
+        sp.a = *args; sp.tables = h->d_tables; sp.t = h->t; sp.g = h->g;
+        sp.ocells64 = reinterpret_cast<const uint64_t *>(h->d_small);
+        const int pi = h->g.P == 4 ? 1 : 0;
+        const int sgrid = grid_for(args->n_roots * args->per_root, h->sks.roll_threads, h->sm_count, h->small_roll_blocks_per_sm);
+        h->sks.rollout[pi]<<<sgrid, h->sks.roll_threads, h->sks.roll_smem, static_cast<cudaStream_t>(stream)>>>(sp);
+        CUDA_TRY(cudaGetLastError());
+        return BLK_OK;
+    }
     RParams rp;
     rp.a = *args; rp.tables = h->d_tables; rp.t = h->t; rp.g = h->g;
     rp.queue = h->d_queue + 2 * (h->launch_seq++ % kQueueSlots);

@@ -960,10 +960,20 @@ struct SmallParams {
     const uint32_t *first_mask;   // legal mask words of the fresh board (player 0's first move)
     int first_count;
 };
+struct SmallRollParams {
+    blk_rollout_args a;
+    const unsigned char *tables;
+    TableLayout t;
+    Geometry g;
+    const uint64_t *ocells64;
+};
 using SmallStepFn = void (*)(const SmallParams);
+using SmallRollFn = void (*)(const SmallRollParams);
 struct SmallKernelSet {
     SmallStepFn step[2][3][2];    // [P == 4][mask format: none, bits, bytes (aligned rows)][sampler]
+    SmallRollFn rollout[2];       // [P == 4] thread-per-playout
     int smem[2], threads[2];
+    int roll_smem, roll_threads;
     int num_actions;
 };
 SmallKernelSet kernels_small_5();

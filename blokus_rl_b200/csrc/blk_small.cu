@@ -413,6 +413,167 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, kP == 2 ? 2 : 3) small_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// playouts on small boards: one THREAD plays one game to the end (or to `stop_player`'s turn); state in registers,
+// the mover's mask words in the thread's shared-memory row (the k-th legal action is looked up there).  Same Philox
+// stream, same "k-th legal action in ascending id order" rule as rollout_kernel, so the two produce identical games.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRT = 256;           // playouts per block
+
+template <int kN, int kP>
+__global__ void __launch_bounds__(kRT, 2) small_rollout_kernel(const SmallRollParams rp) {
+    static_assert(kN == kSN, "one translation unit per board size");
+    constexpr int N = kSN, P = kP;
+    constexpr int SW = P * N + P + 4, kMeta = P * N + P;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem_raw);            // [kRT][kSRS]
+    uint16_t *s_ck = reinterpret_cast<uint16_t *>(s_mask + kRT * kSRS);   // [kRT][4]
+    int32_t *s_obase = reinterpret_cast<int32_t *>(s_ck + 4 * kRT);       // [92]
+    uint32_t *s_oinfo = reinterpret_cast<uint32_t *>(s_obase + 92);       // [92]
+    uint64_t *s_ocells = reinterpret_cast<uint64_t *>(s_oinfo + 92);      // [92]
+    const blk_rollout_args &a = rp.a;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 92; i += kRT) {
+        s_obase[i] = reinterpret_cast<const int32_t *>(rp.tables + rp.t.off_obase)[i];
+        s_oinfo[i] = i < kOrients ? reinterpret_cast<const uint32_t *>(rp.tables + rp.t.off_oinfo)[i] : 0u;
+        s_ocells[i] = i < kOrients ? rp.ocells64[i] : 0ull;
+    }
+    __syncthreads();
+    uint32_t *row = s_mask + tid * kSRS;
+    uint16_t *ck = s_ck + 4 * tid;
+    const int64_t total = a.n_roots * a.per_root;
+    for (int64_t gid = static_cast<int64_t>(blockIdx.x) * kRT + tid; gid < total; gid += static_cast<int64_t>(gridDim.x) * kRT) {
+        const int64_t root = gid / a.per_root;
+        const uint32_t *src = a.roots + root * SW;
+        uint64_t own[P];
+        uint32_t inv[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            uint32_t rows[N];
+#pragma unroll
+            for (int y = 0; y < N; ++y) rows[y] = __ldg(src + q * N + y);
+            own[q] = rows_to_board(rows);
+            inv[q] = __ldg(src + P * N + q);
+        }
+        uint32_t meta = __ldg(src + kMeta), game = __ldg(src + kMeta + 1);
+        uint32_t sc01 = __ldg(src + kMeta + 2), sc23 = __ldg(src + kMeta + 3);
+        const uint32_t key0 = static_cast<uint32_t>(a.seed);
+        const uint32_t key1 = static_cast<uint32_t>(a.seed >> 32) ^ (a.rollout_id_base + static_cast<uint32_t>(gid));
+        int nply = 0, rnd_block = -1;
+        uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+        bool over = (meta >> 4) & 1u;
+        int cand = static_cast<int>(meta & 15u);
+        cand = cand == 0 ? P - 1 : cand - 1;          // the root's mover is evaluated first
+        int tries = 1;
+        uint32_t stuck = 0u;
+        while (!over) {
+            cand = (cand + 1 == P) ? 0 : cand + 1;
+            int cnt = 0;
+            if (!((stuck >> cand) & 1u)) {
+                uint64_t occ = 0ull, mine = own[0];
+                uint32_t invc = inv[0];
+#pragma unroll
+                for (int q = 0; q < P; ++q) {
+                    occ |= own[q];
+                    if (q == cand) { mine = own[q]; invc = inv[q]; }
+                }
+                uint64_t fr, dg;
+                small_prep<P>(mine, occ, invc == kFullInv, cand, fr, dg);
+                if ((fr & dg) != 0ull) cnt = small_eval(fr, dg, invc, row, ck);
+                // a player without a move never gets one back: it is not evaluated again in this playout
+                if (cnt == 0) stuck |= 1u << cand;
+            }
+            if (cnt == 0) {
+                if (--tries > 0) continue;
+                meta |= 1u << 4;
+                over = true;
+                break;
+            }
+            meta = (meta & ~15u) | static_cast<uint32_t>(cand);
+            if (cand == a.stop_player) break;              // caller's turn: hand the state back
+            const uint32_t ply = meta >> 16;
+            if (static_cast<int>(ply >> 2) != rnd_block) {
+                rnd = philox4(ply >> 2, game, 1u, 0u, key0, key1);
+                rnd_block = static_cast<int>(ply >> 2);
+            }
+            int k = static_cast<int>(__umulhi(philox_word(rnd, ply), static_cast<uint32_t>(cnt)));
+            int w = 0;
+#pragma unroll
+            for (int j = kSCk - 1; j >= 0; --j) {
+                const int cj = ck[j];
+                if (w == 0 && k >= cj) { w = 16 * (j + 1); k -= cj; }
+            }
+            uint32_t word = row[w];
+            for (;;) {
+                const int c = __popc(word);
+                if (k < c) break;
+                k -= c;
+                word = row[++w];
+            }
+            const int act = (w << 5) + kth_set_bit(word, k);
+            if (a.action_log != nullptr && nply < a.log_stride - 1) a.action_log[gid * a.log_stride + nply] = static_cast<uint16_t>(act);
+            // decode and place (the action is legal by construction)
+            int lo = 0, hi = kOrients - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_obase[mid] <= act) lo = mid; else hi = mid - 1;
+            }
+            const uint32_t oi = s_oinfo[lo];
+            const int piece = oi & 31, wd = (oi >> 12) & 15, ncells = (oi >> 16) & 15;
+            const int W = N + 1 - wd;
+            const int rem = act - s_obase[lo];
+            const int ay = rem / W, ax = rem - ay * W;
+            const uint64_t pm = s_ocells[lo] << (8 * ay + ax);
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+                if (q == cand) { own[q] |= pm; inv[q] &= ~(1u << piece); }
+            uint32_t &sc = (cand < 2) ? sc01 : sc23;
+            const int sh = 16 * (cand & 1);
+            sc = (sc & ~(0xffffu << sh)) | (((((sc >> sh) & 0xffffu) + ncells) & 0xffffu) << sh);
+            meta = (meta & ~(1u << (8 + cand))) | ((piece == 0 ? 1u : 0u) << (8 + cand));
+            meta += 1u << 16;
+            ++nply;
+            tries = P;
+        }
+        // results: final scores (R10), winners, 3 / 1 / -1 vector (blokus_wrapper.py:177-185)
+        int fs[P], best = -32768, nbest = 0;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const uint32_t packed = q < 2 ? sc01 : sc23;
+            int v = static_cast<int>(static_cast<int16_t>((packed >> (16 * (q & 1))) & 0xffffu));
+            if (rp.g.score_rule == 1 && inv[q] == 0u) v += 15 + (((meta >> (8 + q)) & 1u) ? 5 : 0);
+            fs[q] = v;
+            if (v > best) { best = v; nbest = 1; } else if (v == best) ++nbest;
+        }
+        uint32_t win = 0u;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const bool mine = fs[q] == best;
+            if (mine) win |= 1u << q;
+            if (a.final_scores != nullptr) a.final_scores[gid * P + q] = static_cast<int16_t>(fs[q]);
+            if (a.value_sum != nullptr && over) atomicAdd(a.value_sum + root * P + q, mine ? (nbest == 1 ? 3.f : 1.f) : -1.f);
+        }
+        if (a.state_out != nullptr) {
+            uint32_t *dst = a.state_out + gid * SW;
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+                uint32_t rows[N];
+                board_to_rows(own[q], rows);
+#pragma unroll
+                for (int y = 0; y < N; ++y) dst[q * N + y] = rows[y];
+                dst[P * N + q] = inv[q];
+            }
+            dst[kMeta] = meta; dst[kMeta + 1] = game; dst[kMeta + 2] = sc01; dst[kMeta + 3] = sc23;
+        }
+        if (a.winners != nullptr) a.winners[gid] = over ? static_cast<uint8_t>(win) : 0;
+        if (a.plies != nullptr) a.plies[gid] = nply;
+        if (a.action_log != nullptr) a.action_log[gid * a.log_stride + min(nply, a.log_stride - 1)] = 0xFFFFu;
+    }
+}
+
+static int small_roll_smem_bytes() { return 4 * kRT * kSRS + 8 * kRT + 4 * 92 + 4 * 92 + 8 * 92 + 16; }
+
 static int small_smem_bytes(int P) {
     const int T = P == 2 ? kST2 : kST4;
     const int SWP = (P * kSN + P + 4) | 1;
@@ -432,6 +593,8 @@ SmallKernelSet BLK_SCAT(BLK_SMALL_N)() {
     k.step[1][0][0] = small_step_kernel<kSN, 4, 0, false>; k.step[1][0][1] = small_step_kernel<kSN, 4, 0, true>;
     k.step[1][1][0] = small_step_kernel<kSN, 4, 1, false>; k.step[1][1][1] = small_step_kernel<kSN, 4, 1, true>;
     k.step[1][2][0] = small_step_kernel<kSN, 4, 2, false>; k.step[1][2][1] = small_step_kernel<kSN, 4, 2, true>;
+    k.rollout[0] = small_rollout_kernel<kSN, 2>; k.rollout[1] = small_rollout_kernel<kSN, 4>;
+    k.roll_smem = small_roll_smem_bytes(); k.roll_threads = kRT;
     return k;
 }
 

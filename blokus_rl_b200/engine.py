@@ -260,7 +260,8 @@ class BlokusEngine:
 
     # ---- kernel family 4: uniform-random playouts to the end of the game ---------------------------------
     def rollout(self, roots: torch.Tensor, per_root: int, seed: int = 0, rollout_id_base: int = 0,
-                log_actions: bool = False, stop_player: int = -1, out_states: torch.Tensor | None = None) -> RolloutOut:
+                log_actions: bool = False, stop_player: int = -1, out_states: torch.Tensor | None = None,
+                warp_kernels: bool = False) -> RolloutOut:
         """Uniform-random playouts.  ``stop_player = q`` stops each playout as soon as it is player q's turn (or
         the game is over) and ``out_states`` (may alias ``roots`` when ``per_root == 1``) receives the states
         reached: this is how the gym adapter plays the random-bot opponents inside one ``step``."""
@@ -279,7 +280,8 @@ class BlokusEngine:
         args = _lib.BlkRolloutArgs(n, roots.data_ptr(), per_root, seed & 0xFFFFFFFFFFFFFFFF, rollout_id_base & 0xFFFFFFFF,
                                    final_scores.data_ptr(), winners.data_ptr(), value_sum.data_ptr(),
                                    None if log is None else log.data_ptr(), log_stride, plies.data_ptr(),
-                                   int(stop_player), None if out_states is None else out_states.data_ptr())
+                                   int(stop_player), None if out_states is None else out_states.data_ptr(),
+                                   BLK_OPT_WARP_KERNELS if warp_kernels else 0)
         if total:
             _lib.check(self._lib.blk_rollout(self._h, C.byref(args), self._stream()))
         return RolloutOut(final_scores, winners, value_sum, plies, log)

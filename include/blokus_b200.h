@@ -116,6 +116,7 @@ typedef struct {
     int32_t stop_player;        /* -1: play to the end of the game; q: stop as soon as it is player q's turn (random-bot
                                    opponents inside a gym step: docs/README.md:47-51 of the reference) */
     uint32_t *state_out;        /* nullable [n_roots*per_root][state_words]: the state each playout stopped in */
+    uint32_t options;           /* BLK_OPT_WARP_KERNELS or 0 */
 } blk_rollout_args;
 
 const char *blk_last_error(void);

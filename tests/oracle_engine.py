@@ -112,7 +112,8 @@ class OracleEngine:
         scores = torch.from_numpy(np.stack([self.orc.final_scores(s)[: self.num_players] for s in sts]))
         return flags, term, scores
 
-    def rollout(self, roots, per_root, seed=0, rollout_id_base=0, log_actions=False, stop_player=-1, out_states=None):
+    def rollout(self, roots, per_root, seed=0, rollout_id_base=0, log_actions=False, stop_player=-1, out_states=None,
+                warp_kernels=False):
         orc, P = self.orc, self.num_players
         sts = self._unpack(roots)
         n = len(sts)

@@ -116,3 +116,47 @@ def test_mask_only_and_finished_states_small(engine7, oracle7):
     assert (s == keep).all() and bool((o3.flags == 3).all())
     bits = unpack_bits(o3.mask.cpu().numpy(), eng.num_actions)
     assert bits.sum() == 0
+
+
+@pytest.mark.parametrize("n,p", [(7, 2), (7, 4), (5, 2), (6, 4)])
+def test_small_playouts_equal_warp_playouts_and_oracle(n, p):
+    """Thread-per-playout kernel vs the warp-per-playout kernel (BLK_OPT_WARP_KERNELS): identical action logs, plies, final
+    scores, winners and value sums; a sample of the logs is also replayed through the oracle (same Philox stream)."""
+    import torch
+    from blokus_rl_b200 import BlokusEngine
+    from oracle.oracle import Oracle
+    eng, orc = BlokusEngine(n, p), Oracle(n, p)
+    n_roots, per_root, seed = 96, 40, 0xFACE + n
+    roots = eng.new_states(n_roots)
+    out = eng.step(roots, None, mask=None, sample=True, seed=4)
+    for _ in range(2):
+        out = eng.step(roots, out.next_action, mask=None, sample=True, seed=4)
+    a = eng.rollout(roots, per_root, seed=seed, rollout_id_base=77, log_actions=True)
+    b = eng.rollout(roots, per_root, seed=seed, rollout_id_base=77, log_actions=True, warp_kernels=True)
+    torch.cuda.synchronize()
+    assert (a.plies == b.plies).all() and (a.final_scores == b.final_scores).all() and (a.winners == b.winners).all()
+    assert torch.allclose(a.value_sum, b.value_sum)
+    la, lb = a.action_log.cpu().numpy().view(np.uint16), b.action_log.cpu().numpy().view(np.uint16)
+    pl = a.plies.cpu().numpy()
+    for r in range(n_roots):
+        for j in range(per_root):
+            assert (la[r, j, : pl[r, j] + 1] == lb[r, j, : pl[r, j] + 1]).all()
+    words = roots.cpu().numpy().view(np.uint32)
+    fs, win = a.final_scores.cpu().numpy(), a.winners.cpu().numpy()
+    for r in range(0, n_roots, 7):
+        for j in (0, per_root - 1):
+            o = orc.unpack(words[r])
+            k = 0
+            while not orc.field(o, "done"):
+                act = int(la[r, j, k])
+                assert act == orc.sample_action(o, seed, 77 + r * per_root + j, stream=1)
+                assert orc.step(o, act, fast=True) == 0
+                k += 1
+            assert la[r, j, k] == 0xFFFF and pl[r, j] == k
+            assert (fs[r, j] == orc.final_scores(o)[:p]).all() and win[r, j] == orc.winners(o)
+    # stop_player: hand the state back at the agent's turn (the gym adapter's opponent moves), in place
+    sa, sb = roots.clone(), roots.clone()
+    eng.rollout(sa, 1, seed=9, stop_player=0, out_states=sa)
+    eng.rollout(sb, 1, seed=9, stop_player=0, out_states=sb, warp_kernels=True)
+    assert (sa == sb).all()
+    eng.close()
