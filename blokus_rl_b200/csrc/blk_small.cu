@@ -6,7 +6,7 @@
 // row 7 are zero padding, so shifted reads never wrap into a neighbouring row), which makes an orientation's
 // legality at ALL anchors a chain of 64-bit ANDs / ORs over shifted copies of the "free" and "diagonal contact"
 // boards -- 32 envs per warp instruction instead of one env per warp with 7 of 32 lanes busy (the warp-per-env
-// kernel in blk_kernels.cuh, which stays the path for N >= 8, unaligned byte masks and index lists).
+// kernel in blk_kernels.cuh, which stays the path for N >= 8 and for index-list masks).
 // The action-id-ordered mask words are assembled in registers by straight-line code whose bit positions are all
 // compile-time constants (blk_small_fields.inc, generated) and parked in shared memory; the block then streams
 // states and masks to HBM cooperatively (coalesced 16 B stores through the same byte LUT as the big kernel).
@@ -408,6 +408,27 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, kP == 2 ? 2 : 3) small_
                     BLK_STORE16(reinterpret_cast<uint4 *>(out + 16 * c), make_uint4(lo.x, lo.y, hi.x, hi.y));
                 }
             }
+        } else if (kFmt == 3) {
+            // caller buffer with any base / row stride (e.g. a contiguous bool [n, A]): byte stores up to the first 16 B
+            // boundary and after the last one, chunk-aligned 16 B stores in between (the 16 mask bits of a chunk are
+            // cut out of two neighbouring words with a funnel shift); bytes of neighbouring rows are never touched
+            const unsigned char *lutb = reinterpret_cast<const unsigned char *>(s_lut);
+            for (int slot = warp; slot < m; slot += T / 32) {
+                unsigned char *urow = reinterpret_cast<unsigned char *>(a.mask) + (base + slot) * a.mask_stride;
+                const uint32_t *r = (s_ctl[slot] & kCtlFresh) ? s_first : s_mask + slot * kSRS;
+                const int head = static_cast<int>((16u - (reinterpret_cast<uintptr_t>(urow) & 15u)) & 15u);
+                if (lane < head) urow[lane] = static_cast<unsigned char>((r[0] >> lane) & 1u);
+                const int nchunks = (kSA - head) >> 4;
+                for (int c = lane; c < nchunks; c += 32) {
+                    const int bit0 = head + 16 * c, w = bit0 >> 5;
+                    const uint32_t bits = __funnelshift_r(r[w], w + 1 < kSMW ? r[w + 1] : 0u, bit0 & 31) & 0xffffu;
+                    const uint2 lo = *reinterpret_cast<const uint2 *>(lutb + ((bits << 3) & 0x7f8u));
+                    const uint2 hi = *reinterpret_cast<const uint2 *>(lutb + ((bits >> 5) & 0x7f8u));
+                    BLK_STORE16(reinterpret_cast<uint4 *>(urow + bit0), make_uint4(lo.x, lo.y, hi.x, hi.y));
+                }
+                const int b = head + 16 * nchunks + lane;
+                if (b < kSA) urow[b] = static_cast<unsigned char>((r[b >> 5] >> (b & 31)) & 1u);
+            }
         }
         __syncthreads();
     }
@@ -593,6 +614,8 @@ SmallKernelSet BLK_SCAT(BLK_SMALL_N)() {
     k.step[1][0][0] = small_step_kernel<kSN, 4, 0, false>; k.step[1][0][1] = small_step_kernel<kSN, 4, 0, true>;
     k.step[1][1][0] = small_step_kernel<kSN, 4, 1, false>; k.step[1][1][1] = small_step_kernel<kSN, 4, 1, true>;
     k.step[1][2][0] = small_step_kernel<kSN, 4, 2, false>; k.step[1][2][1] = small_step_kernel<kSN, 4, 2, true>;
+    k.step[0][3][0] = small_step_kernel<kSN, 2, 3, false>; k.step[0][3][1] = small_step_kernel<kSN, 2, 3, true>;
+    k.step[1][3][0] = small_step_kernel<kSN, 4, 3, false>; k.step[1][3][1] = small_step_kernel<kSN, 4, 3, true>;
     k.rollout[0] = small_rollout_kernel<kSN, 2>; k.rollout[1] = small_rollout_kernel<kSN, 4>;
     k.roll_smem = small_roll_smem_bytes(); k.roll_threads = kRT;
     return k;
