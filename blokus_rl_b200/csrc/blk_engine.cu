@@ -429,7 +429,7 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
             blk_destroy(h); return fail(BLK_ERR_CUDA, "small-board table upload failed");
         }
         const int pi = P == 4 ? 1 : 0;
-        for (int f = 0; f < 4; ++f)
+        for (int f = 0; f < 5; ++f)
             for (int sm = 0; sm < 2; ++sm)
                 if (cudaFuncSetAttribute(h->sks.step[pi][f][sm], cudaFuncAttributeMaxDynamicSharedMemorySize, h->sks.smem[pi]) != cudaSuccess) {
                     blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed for the small-board kernels");
@@ -515,7 +515,7 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
         variant = 3;
     const bool bits_rows_8b = variant != BLK_MASK_BITS ||
                               ((args->mask_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(args->mask) & 7) == 0);
-    if (h->small && variant <= 3 && bits_rows_8b && !(args->options & BLK_OPT_WARP_KERNELS)) {
+    if (h->small && bits_rows_8b && !(args->options & BLK_OPT_WARP_KERNELS)) {
         // N <= 7: one env per thread on 64-bit bitboards (blk_small.cu); the other formats stay on the warp-per-env kernel
         SmallParams sp;
         sp.a = *args; sp.tables = h->d_tables; sp.t = h->t; sp.g = h->g;

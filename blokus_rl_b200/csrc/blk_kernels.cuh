@@ -970,7 +970,7 @@ struct SmallRollParams {
 using SmallStepFn = void (*)(const SmallParams);
 using SmallRollFn = void (*)(const SmallRollParams);
 struct SmallKernelSet {
-    SmallStepFn step[2][4][2];    // [P == 4][mask format: none, bits, bytes (aligned rows), bytes (any rows)][sampler]
+    SmallStepFn step[2][5][2];    // [P == 4][mask format: none, bits, bytes (aligned rows), bytes (any rows), ids][sampler]
     SmallRollFn rollout[2];       // [P == 4] thread-per-playout
     int smem[2], threads[2];
     int roll_smem, roll_threads;

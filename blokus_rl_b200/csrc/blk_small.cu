@@ -6,7 +6,7 @@
 // row 7 are zero padding, so shifted reads never wrap into a neighbouring row), which makes an orientation's
 // legality at ALL anchors a chain of 64-bit ANDs / ORs over shifted copies of the "free" and "diagonal contact"
 // boards -- 32 envs per warp instruction instead of one env per warp with 7 of 32 lanes busy (the warp-per-env
-// kernel in blk_kernels.cuh, which stays the path for N >= 8 and for index-list masks).
+// kernel in blk_kernels.cuh, which stays the path for N >= 8).
 // The action-id-ordered mask words are assembled in registers by straight-line code whose bit positions are all
 // compile-time constants (blk_small_fields.inc, generated) and parked in shared memory; the block then streams
 // states and masks to HBM cooperatively (coalesced 16 B stores through the same byte LUT as the big kernel).
@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, kP == 2 ? 2 : 3) small_
                 a.next_action[env] = pick;
             }
             if (a.flags != nullptr)
-                a.flags[env] = static_cast<uint8_t>((ended ? BLK_FLAG_DONE : 0) | ((ctl & kCtlIllegal) ? BLK_FLAG_ILLEGAL : 0));
+                a.flags[env] = static_cast<uint8_t>((ended ? BLK_FLAG_DONE : 0) | ((ctl & kCtlIllegal) ? BLK_FLAG_ILLEGAL : 0) |
+                                                    ((kFmt == 4 && cnt > a.mask_stride) ? BLK_FLAG_TRUNCATED : 0));
             int fs[4], best = -32768, nbest = 0;
 #pragma unroll
             for (int q = 0; q < P; ++q) {
@@ -428,6 +429,28 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, kP == 2 ? 2 : 3) small_
                 }
                 const int b = head + 16 * nchunks + lane;
                 if (b < kSA) urow[b] = static_cast<unsigned char>((r[b >> 5] >> (b & 31)) & 1u);
+            }
+        } else if (kFmt == 4) {
+            // sparse form: the ascending legal ids as uint16 (ppo/trainer.py:385 reads these lists); lane l's word precedes
+            // lane l + 1's, so an exclusive scan of the per-lane popcounts gives every lane its slots
+            for (int slot = warp; slot < m; slot += T / 32) {
+                uint16_t *irow = reinterpret_cast<uint16_t *>(a.mask) + (base + slot) * a.mask_stride;
+                const uint32_t *r = (s_ctl[slot] & kCtlFresh) ? s_first : s_mask + slot * kSRS;
+                int ibase = 0;
+                for (int w0 = 0; w0 < kSMW; w0 += 32) {
+                    const int w = w0 + lane;
+                    uint32_t word = w < kSMW ? r[w] : 0u;
+                    const int pc = __popc(word);
+                    const int incl = warp_incl_scan(pc, lane);
+                    int pos = ibase + incl - pc;
+                    while (word) {
+                        const int id = (w << 5) + __ffs(word) - 1;
+                        word &= word - 1;
+                        if (pos < a.mask_stride) irow[pos] = static_cast<uint16_t>(id);
+                        ++pos;
+                    }
+                    ibase += __shfl_sync(kAllLanes, incl, 31);
+                }
             }
         }
         __syncthreads();
@@ -616,6 +639,8 @@ SmallKernelSet BLK_SCAT(BLK_SMALL_N)() {
     k.step[1][2][0] = small_step_kernel<kSN, 4, 2, false>; k.step[1][2][1] = small_step_kernel<kSN, 4, 2, true>;
     k.step[0][3][0] = small_step_kernel<kSN, 2, 3, false>; k.step[0][3][1] = small_step_kernel<kSN, 2, 3, true>;
     k.step[1][3][0] = small_step_kernel<kSN, 4, 3, false>; k.step[1][3][1] = small_step_kernel<kSN, 4, 3, true>;
+    k.step[0][4][0] = small_step_kernel<kSN, 2, 4, false>; k.step[0][4][1] = small_step_kernel<kSN, 2, 4, true>;
+    k.step[1][4][0] = small_step_kernel<kSN, 4, 4, false>; k.step[1][4][1] = small_step_kernel<kSN, 4, 4, true>;
     k.rollout[0] = small_rollout_kernel<kSN, 2>; k.rollout[1] = small_rollout_kernel<kSN, 4>;
     k.roll_smem = small_roll_smem_bytes(); k.roll_threads = kRT;
     return k;

@@ -160,3 +160,29 @@ def test_small_playouts_equal_warp_playouts_and_oracle(n, p):
     eng.rollout(sb, 1, seed=9, stop_player=0, out_states=sb, warp_kernels=True)
     assert (sa == sb).all()
     eng.close()
+
+
+def test_index_lists_small(engine7, oracle7):
+    """BLK_MASK_INDICES on the thread-per-env kernel: ascending legal ids, counts, truncation flag; equal to the warp kernel."""
+    import torch
+    eng = engine7
+    n = 777
+    s = eng.new_states(n)
+    out = eng.step(s, None, mask="bytes", sample=True, seed=6)
+    for _ in range(5):
+        out = eng.step(s, out.next_action, mask="bytes", sample=True, seed=6, auto_reset=True)
+    a = eng.step(s, None, mask="indices")
+    b = eng.step(s, None, mask="indices", warp_kernels=True)
+    torch.cuda.synchronize()
+    ids, cnt = a.mask.cpu().numpy().view(np.uint16), a.legal_count.cpu().numpy()
+    idb = b.mask.cpu().numpy().view(np.uint16)
+    dense = out.mask.cpu().numpy()
+    assert (a.legal_count == b.legal_count).all() and (a.flags == b.flags).all()
+    for i in range(n):
+        assert ids[i, : cnt[i]].tolist() == np.flatnonzero(dense[i]).tolist() == idb[i, : cnt[i]].tolist()
+    fresh = eng.new_states(3)
+    small = torch.zeros((3, 10), dtype=torch.int16, device=s.device)
+    o2 = eng.step(fresh, None, mask=small)
+    first = np.flatnonzero(oracle7.legal_mask(oracle7.new_state()))
+    assert (o2.flags.cpu().numpy() & 4).all() and (o2.legal_count.cpu().numpy() == 58).all()
+    assert small[2].cpu().numpy().view(np.uint16).tolist() == first[:10].tolist()
