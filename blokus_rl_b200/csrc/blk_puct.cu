@@ -44,10 +44,23 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_select_kernel(blk_pu
         const double sq = __dsqrt_rn(__dadd_rn(s, (eps_fix || depth > 0) ? 1e-6 : 0.0));
         double best = -1.0e300;
         int besti = 0x7fffffff;
-        for (int i = lane; i < n; i += 32) {
-            const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c, f.edge_p[e0 + i]), sq), __dadd_rn(1.0, f.edge_n[e0 + i]));
-            const double sc = __dadd_rn(f.edge_q[e0 + i], u);
-            if (sc > best) { best = sc; besti = i; }            // ascending i per lane: keeps the first maximum
+        for (int i0 = lane; i0 < n; i0 += 128) {               // four edges per lane in flight (12 loads), then the arithmetic
+            double ep[4], en[4], eq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + 32 * k;
+                const bool in = i < n;
+                ep[k] = in ? __ldg(f.edge_p + e0 + i) : 0.0;
+                en[k] = in ? __ldg(f.edge_n + e0 + i) : 0.0;
+                eq[k] = in ? __ldg(f.edge_q + e0 + i) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + 32 * k;
+                const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c, ep[k]), sq), __dadd_rn(1.0, en[k]));
+                const double sc = __dadd_rn(eq[k], u);
+                if (i < n && sc > best) { best = sc; besti = i; }   // ascending i per lane: keeps the first maximum
+            }
         }
 #pragma unroll
         for (int d = 16; d; d >>= 1) {
