@@ -123,9 +123,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
     // pool slot of this tree's new state: explicit base, or the device-side counter (CUDA-graph friendly)
     const int slot = (a.new_slot_base >= 0 ? a.new_slot_base : f.counters[4]) + t;
     if (slot >= f.node_capacity) { if (lane == 0) f.counters[2] = 1; if (lane < P) score[lane] = 0.0; return; }
-    if (a.pool != nullptr)
-        for (int i = lane; i < a.state_words; i += 32)
-            a.pool[static_cast<int64_t>(slot) * a.state_words + i] = a.new_states[static_cast<int64_t>(t) * a.state_words + i];
+    if (a.pool != nullptr) {
+        uint32_t sv[4];                                     // state_words <= 88 at 20x20/4p: at most 3 words per lane, loads first
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; sv[k] = i < a.state_words ? __ldg(a.new_states + static_cast<int64_t>(t) * a.state_words + i) : 0u; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < a.state_words) a.pool[static_cast<int64_t>(slot) * a.state_words + i] = sv[k]; }
+    }
     if (st == BLK_PUCT_NEED_STEP) {
         const uint8_t fl = a.flags[t];
         int node = 0;
@@ -160,15 +164,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
     const int rounds = (nwords + 31) >> 5;                       // <= 32 words per lane
     uint32_t *words = s_words[warp];
     if (a.mask_bits) {
-        // bit-packed rows: independent coalesced loads, six in flight per lane (a plain loop waits out the full memory
+        // bit-packed rows: independent coalesced loads, ten in flight per lane (a plain loop waits out the full memory
         // latency once per 128 B)
         const uint32_t *rw = reinterpret_cast<const uint32_t *>(row);
-        for (int r0 = 0; r0 < rounds; r0 += 6) {
-            uint32_t v[6];
+        for (int r0 = 0; r0 < rounds; r0 += 10) {
+            uint32_t v[10];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { const int g = ((r0 + k) << 5) + lane; v[k] = (r0 + k < rounds && g < nwords) ? __ldg(rw + g) : 0u; }
+            for (int k = 0; k < 10; ++k) { const int g = ((r0 + k) << 5) + lane; v[k] = (r0 + k < rounds && g < nwords) ? __ldg(rw + g) : 0u; }
 #pragma unroll
-            for (int k = 0; k < 6; ++k) if (r0 + k < rounds) words[((r0 + k) << 5) + lane] = v[k];
+            for (int k = 0; k < 10; ++k) if (r0 + k < rounds) words[((r0 + k) << 5) + lane] = v[k];
         }
     }
     for (int r = 0; r < (a.mask_bits ? 0 : rounds); ++r) {
