@@ -503,6 +503,8 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
             return fail(BLK_ERR_ARG, "BLK_MASK_INDICES needs legal_count and a positive mask_stride");
     }
     if (args->obs && (reinterpret_cast<uintptr_t>(args->obs) & 15) != 0) return fail(BLK_ERR_ARG, "obs must be 16 B aligned");
+    if (args->state_index && (!args->state_out || args->state_out == args->state_in))
+        return fail(BLK_ERR_ARG, "state_index needs a separate state_out");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     KParams kp;
     kp.a = *args; kp.tables = h->d_tables; kp.t = h->t; kp.g = h->g;

@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
     EnvRaw raw_next = {};
     int act_next = BLK_ACTION_NONE;
     if (env < n) {
-        raw_next = env_fetch(a.state_in + env * sw, g, lane);
+        raw_next = env_fetch(a.state_in + (a.state_index != nullptr ? __ldg(a.state_index + env) : env) * sw, g, lane);
         if (a.action != nullptr) act_next = __ldg(a.action + env);
     }
     for (; env < n; env = env_next, env_next = ticket_get(pending)) {
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
         env_unpack(e, raw_next, g);
         const int act = act_next;
         if (env_next < n) {
-            raw_next = env_fetch(a.state_in + env_next * sw, g, lane);
+            raw_next = env_fetch(a.state_in + (a.state_index != nullptr ? __ldg(a.state_index + env_next) : env_next) * sw, g, lane);
             if (a.action != nullptr) act_next = __ldg(a.action + env_next);
         }
         pending = ticket_issue(kp.queue, lane);             // broadcast by the loop increment, one env later

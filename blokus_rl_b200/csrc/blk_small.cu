@@ -179,9 +179,16 @@ __global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, kP == 2 ? 2 : 3) small_
     for (int64_t base = static_cast<int64_t>(blockIdx.x) * T; base < n; base += static_cast<int64_t>(gridDim.x) * T) {
         const int m = static_cast<int>(min(static_cast<int64_t>(T), n - base));
         // ---- phase 0: coalesced load of the block's env states ----
-        for (int i = tid; i < m * SW; i += T) {
-            const int slot = i / SW, w = i - slot * SW;
-            s_state[slot * SWP + w] = __ldg(a.state_in + base * SW + i);
+        if (a.state_index == nullptr) {
+            for (int i = tid; i < m * SW; i += T) {
+                const int slot = i / SW, w = i - slot * SW;
+                s_state[slot * SWP + w] = __ldg(a.state_in + base * SW + i);
+            }
+        } else {                                             // states gathered out of a pool (search trees)
+            for (int i = tid; i < m * SW; i += T) {
+                const int slot = i / SW, w = i - slot * SW;
+                s_state[slot * SWP + w] = __ldg(a.state_in + static_cast<int64_t>(__ldg(a.state_index + base + slot)) * SW + w);
+            }
         }
         if (tid < 2) s_len[tid] = 0;
         __syncthreads();

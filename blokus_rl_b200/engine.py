@@ -134,7 +134,8 @@ class BlokusEngine:
              mask: str | torch.Tensor | None = "bytes", want_count: bool = True, want_terminal: bool = True,
              want_scores: bool = True, sample: bool = False, seed: int = 0, env_id_base: int = 0,
              auto_reset: bool = False, buffers: StepOut | None = None,
-             obs: torch.Tensor | bool | None = None, warp_kernels: bool = False) -> StepOut:
+             obs: torch.Tensor | bool | None = None, warp_kernels: bool = False,
+             state_index: torch.Tensor | None = None) -> StepOut:
         """Apply ``actions`` (or none: mask-only), resolve the next mover with auto-skip, detect the end
         of the game and emit the next mover's full legal mask.  In-place on ``states`` unless
         ``out_states`` is given (functional use, as MCTS needs: blokus_rl/alphazero/mcts.py:47).  ``obs`` (a
@@ -145,11 +146,20 @@ class BlokusEngine:
         self._check_states(states)
         n = states.shape[0]
         dev = self.device
+        if state_index is not None:
+            # env i reads states[state_index[i]] (a search tree stepping states out of its node pool: no gather pass)
+            if state_index.dtype != torch.int32 or state_index.dim() != 1 or state_index.device != dev or not state_index.is_contiguous():
+                raise ValueError("state_index must be a contiguous int32 [n] CUDA tensor")
+            if out_states is None or out_states.data_ptr() == states.data_ptr():
+                raise ValueError("state_index needs separate out_states")
+            n = state_index.shape[0]
         if actions is not None:
             if actions.dtype != torch.int32 or actions.shape != (n,) or actions.device != dev or not actions.is_contiguous():
                 raise ValueError("actions must be a contiguous int32 [n] CUDA tensor")
         out_states = states if out_states is None else out_states
         self._check_states(out_states)
+        if out_states.shape[0] != n:
+            raise ValueError("out_states must have one row per env")
         b = buffers
         raw_mask, fmt, stride = None, BLK_MASK_NONE, 0
         if isinstance(mask, torch.Tensor):
@@ -208,7 +218,7 @@ class BlokusEngine:
             None if scores is None else scores.data_ptr(),
             None if next_action is None else next_action.data_ptr(),
             seed & 0xFFFFFFFFFFFFFFFF, env_id_base & 0xFFFFFFFF, (BLK_OPT_AUTO_RESET if auto_reset else 0) | (BLK_OPT_WARP_KERNELS if warp_kernels else 0),
-            None if obs is None else obs.data_ptr())
+            None if obs is None else obs.data_ptr(), None if state_index is None else state_index.data_ptr())
         _lib.check(self._lib.blk_step(self._h, C.byref(args), self._stream()))
         view = None
         if raw_mask is not None:

@@ -106,9 +106,9 @@ class GpuPuct:
         to a kernel here is the same on every call (new states go through `stage`, their pool slots come from a
         device-side counter), so the sequence can be captured into a CUDA graph."""
         t, B, eng = self.t, self.B, self.eng
-        src = self.pool.index_select(0, t["src_slot"].long())
-        out = eng.step(src, t["step_action"], out_states=self.stage, buffers=self.buf, mask=self.mask_fmt,
-                       want_count=False, want_scores=False, obs=None if attach_only else self.obs)
+        # the parents' states are read straight out of the pool (blk_step_args.state_index): no gather pass
+        out = eng.step(self.pool, t["step_action"], out_states=self.stage, state_index=t["src_slot"], buffers=self.buf,
+                       mask=self.mask_fmt, want_count=False, want_scores=False, obs=None if attach_only else self.obs)
         prior, pd, ps, value = None, 0, 0, None
         if not attach_only and not isinstance(self.evaluator, UniformEvaluator):
             if self.obs is not None:
@@ -127,7 +127,7 @@ class GpuPuct:
                                       out.terminal.data_ptr(), None if prior is None else prior.data_ptr(), pd, ps,
                                       None if value is None else value.data_ptr())
         self._check(self._lib.blk_puct_expand(C.byref(self.forest), C.byref(args), self._stream()))
-        self._keep = (src, prior, value)                 # keep graph-captured temporaries alive
+        self._keep = (prior, value)                      # keep graph-captured temporaries alive
 
     def _simulate_eager(self, cpuct: float, epsilon_fix: bool) -> None:
         self._check(self._lib.blk_puct_select(C.byref(self.forest), float(cpuct), int(epsilon_fix), self._stream()))

@@ -98,6 +98,8 @@ typedef struct {
     float *obs;                 /* nullable [n][2P][N][N] float32, 16 B aligned: canonical_board of the RESULTING state
                                    (blokus_wrapper.py:144-146), written by the same kernel -- leaf expansion for the
                                    policy/value net is then one launch: new state + legal mask + observation */
+    const int32_t *state_index; /* nullable [n]: env i reads state_in[state_index[i]] instead of state_in[i] (a search tree
+                                   stepping states out of its node pool: no gather pass; state_out must not alias state_in) */
 } blk_step_args;
 
 /* Arguments of blk_rollout(): uniform-random playouts to the end of the game, one warp per game. */

@@ -42,7 +42,9 @@ class OracleEngine:
         return None
 
     def step(self, states, actions=None, *, out_states=None, mask="bytes", want_count=True, want_terminal=True,
-             want_scores=True, sample=False, seed=0, env_id_base=0, auto_reset=False, buffers=None, obs=None, warp_kernels=False):
+             want_scores=True, sample=False, seed=0, env_id_base=0, auto_reset=False, buffers=None, obs=None, warp_kernels=False, state_index=None):
+        if state_index is not None:
+            states = states.index_select(0, state_index.long())
         orc, n, P = self.orc, states.shape[0], self.num_players
         sts = self._unpack(states)
         flags = np.zeros(n, np.uint8)

@@ -35,7 +35,7 @@ def test_abi_version_and_struct_sizes(lib):
     from blokus_rl_b200 import _lib
     assert lib.blk_abi_version() == 2
     assert C.sizeof(_lib.BlkConfig) == 16 and C.sizeof(_lib.BlkInfo) == 44
-    assert C.sizeof(_lib.BlkStepArgs) == 120 and C.sizeof(_lib.BlkRolloutArgs) == 112
+    assert C.sizeof(_lib.BlkStepArgs) == 128 and C.sizeof(_lib.BlkRolloutArgs) == 112
 
 
 def test_no_cpu_fallback(lib):

@@ -178,6 +178,32 @@ def test_fused_observation_output(engine20, oracle20, engine7, oracle7):
         engine20.step(engine20.new_states(2), None, obs=torch.empty((2, 8, 20, 19), device="cuda"))
 
 
+def test_state_index_equals_gather(engine20, engine7):
+    """blk_step_args.state_index: env i steps pool[state_index[i]] -- same outputs as gathering the rows first (what the
+    PUCT forest used to do with torch.index_select), the pool itself stays untouched."""
+    import torch
+    for eng in (engine20, engine7):
+        m, n = 500, 333
+        pool = eng.new_states(m)
+        out = eng.step(pool, None, mask=None, sample=True, seed=12)
+        for _ in range(10 if eng.board_size == 20 else 3):
+            out = eng.step(pool, out.next_action, mask=None, sample=True, seed=12)
+        keep = pool.clone()
+        idx = torch.randint(0, m, (n,), device=pool.device, dtype=torch.int32)
+        acts = out.next_action.index_select(0, idx.long()).contiguous()
+        a_dst, b_dst = torch.empty((n, eng.state_words), dtype=torch.int32, device=pool.device), None
+        a = eng.step(pool, acts, out_states=a_dst, state_index=idx, mask="bytes", obs=True)
+        gathered = pool.index_select(0, idx.long())
+        b_dst = torch.empty_like(a_dst)
+        b = eng.step(gathered, acts, out_states=b_dst, mask="bytes", obs=True)
+        torch.cuda.synchronize()
+        assert (pool == keep).all() and (a_dst == b_dst).all() and (a.mask == b.mask).all() and (a.obs == b.obs).all()
+        for name in ("legal_count", "flags", "terminal", "scores"):
+            assert (getattr(a, name) == getattr(b, name)).all()
+        with pytest.raises(ValueError):
+            eng.step(pool, acts, state_index=idx)                    # in place makes no sense with an index
+
+
 def test_unaligned_and_contiguous_bool_mask(engine20, oracle20, engine7):
     """Caller-provided contiguous bool [n, A] buffers (row stride 30,433: every row starts at a different offset inside
     a 16 B chunk) and arbitrarily offset bases give the same masks as the padded layout, and neighbours stay intact."""
