@@ -62,7 +62,7 @@ class BlkPuctForest(C.Structure):
                 [(n, C.c_void_p) for n in ("node_edge0", "node_nedge", "node_state", "node_mover", "node_terminal",
                                            "node_term_value", "edge_action", "edge_child", "edge_n", "edge_q", "edge_p",
                                            "root", "path", "path_len", "status", "leaf_node", "leaf_edge", "src_slot",
-                                           "step_action", "scores", "counters", "node_sum_n", "path_node")])
+                                           "step_action", "scores", "counters", "node_sum_n", "path_node", "node_uniform")])
 
 
 class BlkPuctExpandArgs(C.Structure):
@@ -70,7 +70,7 @@ class BlkPuctExpandArgs(C.Structure):
                 ("attach_only", C.c_int32), ("new_states", C.c_void_p), ("pool", C.c_void_p), ("mask", C.c_void_p),
                 ("mask_bits", C.c_int32), ("mask_stride_words", C.c_int32), ("flags", C.c_void_p),
                 ("terminal", C.c_void_p), ("prior", C.c_void_p), ("prior_dtype", C.c_int32), ("prior_stride", C.c_int64),
-                ("value", C.c_void_p)]
+                ("value", C.c_void_p), ("fuse_backup", C.c_int32)]
 
 
 class EngineError(RuntimeError):

@@ -27,7 +27,14 @@ constexpr uint32_t kAll = 0xffffffffu;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxIds = 1024;      // legal ids compacted per sweep of puct_expand_kernel (20x20 positions have <= ~800)
 
+// A fused expansion (ExpandArgs::fuse_backup) cannot move the pool-slot counter itself -- warps of the same launch still
+// read it -- so it leaves a note and the next kernel that runs before an expansion applies it.
+__device__ __forceinline__ void apply_pending_slot_advance(const blk_puct_forest &f) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && f.counters[5]) { f.counters[4] += f.num_trees; f.counters[5] = 0; }
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_select_kernel(blk_puct_forest f, double cpuct, int eps_fix) {
+    apply_pending_slot_advance(f);
     const int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= f.num_trees) return;
@@ -39,6 +46,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_select_kernel(blk_pu
         if (e0 < 0) { status = BLK_PUCT_NEED_EVAL; src = f.node_state[node]; break; }
         if (len == f.max_depth) { if (lane == 0) f.counters[2] = 1; status = BLK_PUCT_TERMINAL; break; }
         const int n = f.node_nedge[node];
+        const bool uniform = f.node_uniform[node] != 0;           // P = 1/n for every edge: not stored per edge
+        const double pu = __ddiv_rn(1.0, static_cast<double>(n));
         const double s = f.node_sum_n[node];           // sum of the edges' visit counts, maintained by the backup
         const double c = depth == 0 ? cpuct : 1.0;
         const double sq = __dsqrt_rn(__dadd_rn(s, (eps_fix || depth > 0) ? 1e-6 : 0.0));
@@ -50,7 +59,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_select_kernel(blk_pu
             for (int k = 0; k < 4; ++k) {
                 const int i = i0 + 32 * k;
                 const bool in = i < n;
-                ep[k] = in ? __ldg(f.edge_p + e0 + i) : 0.0;
+                ep[k] = uniform ? pu : (in ? __ldg(f.edge_p + e0 + i) : 0.0);
                 en[k] = in ? __ldg(f.edge_n + e0 + i) : 0.0;
                 eq[k] = in ? __ldg(f.edge_q + e0 + i) : 0.0;
             }
@@ -103,15 +112,12 @@ struct ExpandArgs {
     int32_t prior_dtype;          // 0 uniform, 1 float32, 2 float64
     int64_t prior_stride;
     const double *value;          // [B][P]
+    int32_t fuse_backup;          // 1: the expansion warp also walks the path back (no separate blk_puct_backup launch)
 };
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(ExpandArgs a) {
-    __shared__ uint32_t s_words[kWarpsPerBlock][1024];
-    __shared__ uint16_t s_ids[kWarpsPerBlock][kMaxIds];
+// expansion of one tree by one warp (mcts.py:59-71); every exit leaves the simulation's score vector in f.scores
+__device__ __forceinline__ void expand_tree(const ExpandArgs &a, uint32_t *words, uint16_t *ids, int t, int lane) {
     const blk_puct_forest &f = a.f;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * kWarpsPerBlock + warp;
-    if (t >= f.num_trees) return;
     const int P = f.num_players;
     const int st = f.status[t];
     double *score = f.scores + static_cast<int64_t>(t) * P;
@@ -162,7 +168,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
     const uint8_t *row = a.mask + static_cast<int64_t>(t) * mstride * (a.mask_bits ? 4 : 1);
     const int nwords = (f.num_actions + 31) >> 5;
     const int rounds = (nwords + 31) >> 5;                       // <= 32 words per lane
-    uint32_t *words = s_words[warp];
     if (a.mask_bits) {
         // bit-packed rows: independent coalesced loads, ten in flight per lane (a plain loop waits out the full memory
         // latency once per 128 B)
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
     if (lane == 0) e0 = atomicAdd(&f.counters[1], n);
     e0 = __shfl_sync(kAll, e0, 0);
     if (e0 + n > f.edge_capacity) { if (lane == 0) f.counters[2] = 1; if (lane < P) score[lane] = 0.0; return; }
-    if (lane == 0) { f.node_edge0[target] = e0; f.node_nedge[target] = n; f.node_sum_n[target] = 0.0; }
+    if (lane == 0) { f.node_edge0[target] = e0; f.node_nedge[target] = n; f.node_sum_n[target] = 0.0; f.node_uniform[target] = a.prior_dtype == 0; }
     // Two phases so that the edge arrays are written with coalesced warp stores: (1) every lane compacts the ids of its
     // contiguous chunk of mask words into shared memory at its prefix position (ascending id order falls out of the
     // chunk order), (2) the warp sweeps the n edges 32 at a time.  Writing edges straight from the per-lane chunks put
@@ -212,7 +217,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
     // simulation at B >= 4,096; 301 -> 120 us per launch at B = 16,384).  One bump-counter atomic per tree is not the
     // cost: claiming node / edge space once per block of 8 trees instead measured slower (137 us).
     const double uni = n > 0 ? __ddiv_rn(1.0, static_cast<double>(n)) : 0.0;
-    uint16_t *ids = s_ids[warp];
     int done_e = 0;                                        // edges already written (n exceeds kMaxIds only in theory)
     const int skip = incl - mine;                          // this lane's first position in id order
     while (done_e < n) {
@@ -237,12 +241,49 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(Expand
             double p = uni;
             if (a.prior_dtype == 1) p = static_cast<double>(reinterpret_cast<const float *>(a.prior)[t * a.prior_stride + id]);
             else if (a.prior_dtype == 2) p = reinterpret_cast<const double *>(a.prior)[t * a.prior_stride + id];
-            f.edge_action[e] = id; f.edge_child[e] = -1; f.edge_n[e] = 0.0; f.edge_q[e] = 0.0; f.edge_p[e] = p;
+            f.edge_action[e] = id; f.edge_child[e] = -1; f.edge_n[e] = 0.0; f.edge_q[e] = 0.0;
+            if (a.prior_dtype != 0) f.edge_p[e] = p;
         }
         __syncwarp();
         done_e += m;
     }
     if (lane < P) score[lane] = a.value != nullptr ? a.value[t * P + lane] : 0.0;
+}
+
+// running-mean backup along the recorded path (mcts.py:53-57); the path's edges belong to distinct nodes, so the
+// levels are independent: lane d takes level d
+__device__ __forceinline__ void backup_tree(const blk_puct_forest &f, int t, int lane) {
+    const double *score = f.scores + static_cast<int64_t>(t) * f.num_players;
+    const int32_t *path = f.path + static_cast<int64_t>(t) * f.max_depth;
+    const int32_t *pnode = f.path_node + static_cast<int64_t>(t) * f.max_depth;
+    const int len = f.path_len[t];
+    for (int d = lane; d < len; d += 32) {
+        const int e = path[d];
+        const int child = f.edge_child[e];
+        if (child < 0) continue;                                   // capacity overflow: flagged in counters[2]
+        const double val = score[f.node_mover[child]];
+        const double n = f.edge_n[e], q = f.edge_q[e];
+        f.edge_q[e] = __ddiv_rn(__dadd_rn(__dmul_rn(n, q), val), __dadd_rn(n, 1.0));
+        f.edge_n[e] = __dadd_rn(n, 1.0);
+        f.node_sum_n[pnode[d]] = __dadd_rn(f.node_sum_n[pnode[d]], 1.0);     // integer-valued: exact
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_expand_kernel(ExpandArgs a) {
+    __shared__ uint32_t s_words[kWarpsPerBlock][1024];
+    __shared__ uint16_t s_ids[kWarpsPerBlock][kMaxIds];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= a.f.num_trees) return;
+    expand_tree(a, s_words[warp], s_ids[warp], t, lane);
+    if (a.fuse_backup) {
+        // the same warp wrote the score vector and the new child link: order them before the path walk reads them
+        __syncwarp();
+        backup_tree(a.f, t, lane);
+        // this simulation's B pool slots are taken; the counter itself moves in the next select / advance launch, when no
+        // warp of this launch can still be reading it
+        if (t == 0 && lane == 0) a.f.counters[5] = 1;
+    }
 }
 
 __global__ void puct_backup_kernel(blk_puct_forest f) {
@@ -266,6 +307,7 @@ __global__ void puct_backup_kernel(blk_puct_forest f) {
 
 // root <- child of the root edge carrying `action`; children that do not exist yet are requested as NEED_STEP
 __global__ void puct_advance_kernel(blk_puct_forest f, const int32_t *actions) {
+    apply_pending_slot_advance(f);
     const int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= f.num_trees) return;
@@ -347,7 +389,7 @@ int blk_puct_expand(const blk_puct_forest *f, const blk_puct_expand_args *x, voi
     a.attach_only = x->attach_only; a.new_states = x->new_states; a.pool = x->pool; a.mask = x->mask; a.flags = x->flags;
     a.mask_bits = x->mask_bits; a.mask_stride_words = x->mask_stride_words;
     a.terminal = x->terminal; a.prior = x->prior; a.prior_dtype = x->prior_dtype; a.prior_stride = x->prior_stride;
-    a.value = x->value;
+    a.value = x->value; a.fuse_backup = x->fuse_backup;
     const int grid = (f->num_trees + kWarpsPerBlock - 1) / kWarpsPerBlock;
     puct_expand_kernel<<<grid, kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return puct_launch_check();

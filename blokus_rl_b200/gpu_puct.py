@@ -1,7 +1,7 @@
 """Device-resident batched PUCT search: B trees live in GPU arrays and every
-simulation of all B trees is five kernel launches with no host synchronisation:
+simulation of all B trees is three kernel launches (+ the evaluator) with no host synchronisation:
 
-    blk_puct_select  ->  blk_step (opened edges, legal masks)  ->  evaluator  ->  blk_puct_expand  ->  blk_puct_backup
+    blk_puct_select  ->  blk_step (opened edges, legal masks)  ->  evaluator  ->  blk_puct_expand (+ backup, fused)
 
 Per tree the arithmetic is that of ``blokus_rl/alphazero/mcts.py`` in float64 (see csrc/blk_puct.cu for the
 quirks it reproduces); ``tests/test_gpu_puct.py`` checks visit counts / Q / per-simulation score vectors against
@@ -49,8 +49,9 @@ class GpuPuct:
             "path_len": torch.zeros(self.B, **i32), "status": torch.zeros(self.B, **i32),
             "leaf_node": torch.zeros(self.B, **i32), "leaf_edge": torch.zeros(self.B, **i32),
             "src_slot": torch.zeros(self.B, **i32), "step_action": torch.zeros(self.B, **i32),
-            "scores": torch.zeros((self.B, self.P), **f64), "counters": torch.zeros(5, **i32),
+            "scores": torch.zeros((self.B, self.P), **f64), "counters": torch.zeros(6, **i32),
             "node_sum_n": torch.empty(self.node_cap, **f64), "path_node": torch.empty((self.B, max_depth), **i32),
+            "node_uniform": torch.zeros(self.node_cap, dtype=torch.int8, device=dev),
         }
         self.pool = torch.empty((self.node_cap, engine.state_words), dtype=torch.int32, device=dev)
         self.used = 0
@@ -59,7 +60,7 @@ class GpuPuct:
                                              "node_edge0", "node_nedge", "node_state", "node_mover", "node_terminal",
                                              "node_term_value", "edge_action", "edge_child", "edge_n", "edge_q", "edge_p",
                                              "root", "path", "path_len", "status", "leaf_node", "leaf_edge", "src_slot",
-                                             "step_action", "scores", "counters", "node_sum_n", "path_node")])
+                                             "step_action", "scores", "counters", "node_sum_n", "path_node", "node_uniform")])
         # a net needs the dense bool mask; the uniform prior only needs the legal ids, which the 8x smaller
         # bit-packed mask gives just as well
         self.mask_fmt = "bits" if isinstance(self.evaluator, UniformEvaluator) else "bytes"
@@ -98,7 +99,7 @@ class GpuPuct:
         t["node_mover"][:B] = (states[:, self._meta] & 15).to(torch.int8)
         t["node_terminal"][:B] = (flags & 1).to(torch.int8)
         t["node_term_value"][:B] = term.to(torch.float64)
-        t["counters"].copy_(torch.tensor([B, 0, 0, 0, B], dtype=torch.int32))
+        t["counters"].copy_(torch.tensor([B, 0, 0, 0, B, 0], dtype=torch.int32))
 
     # ---- one simulation of every tree ---------------------------------------------------------------------------
     def _step_and_expand(self, attach_only: bool):
@@ -125,14 +126,13 @@ class GpuPuct:
                                       self.pool.data_ptr(), out.mask_raw.data_ptr(), int(self.mask_fmt == "bits"),
                                       eng.mask_words, out.flags.data_ptr(),
                                       out.terminal.data_ptr(), None if prior is None else prior.data_ptr(), pd, ps,
-                                      None if value is None else value.data_ptr())
+                                      None if value is None else value.data_ptr(), 1)      # fused backup
         self._check(self._lib.blk_puct_expand(C.byref(self.forest), C.byref(args), self._stream()))
         self._keep = (prior, value)                      # keep graph-captured temporaries alive
 
     def _simulate_eager(self, cpuct: float, epsilon_fix: bool) -> None:
         self._check(self._lib.blk_puct_select(C.byref(self.forest), float(cpuct), int(epsilon_fix), self._stream()))
-        self._step_and_expand(False)
-        self._check(self._lib.blk_puct_backup(C.byref(self.forest), self._stream()))
+        self._step_and_expand(False)                     # the expansion launch also walks the paths back
 
     def simulate(self, cpuct: float = 1.0, epsilon_fix: bool = True) -> None:
         """One simulation of every tree.  After two eager runs the launch sequence is captured into a CUDA graph
@@ -154,7 +154,7 @@ class GpuPuct:
             self._simulate_eager(cpuct, epsilon_fix)
             self._eager_runs += 1
         self.used += self.B
-        self.launches += 5
+        self.launches += 3
 
     def advance(self, actions: torch.Tensor) -> None:
         """Make the child under ``actions[t]`` the root of tree t (``-1`` leaves a tree where it is)."""
@@ -162,8 +162,7 @@ class GpuPuct:
         if self.used + self.B > self.node_cap:
             raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
         self._check(self._lib.blk_puct_advance(C.byref(self.forest), acts.data_ptr(), self._stream()))
-        self._step_and_expand(True)
-        self._check(self._lib.blk_puct_backup(C.byref(self.forest), self._stream()))   # empty paths: only takes the pool slots
+        self._step_and_expand(True)                      # empty paths: the fused backup only takes the pool slots
         self.used += self.B
 
     # ---- results (host side; synchronises) ---------------------------------------------------------------------------
@@ -191,6 +190,11 @@ class GpuPuct:
         di = torch.as_tensor(idx, device=root.device, dtype=torch.long)
         cols = [self.t[k].index_select(0, di).cpu().numpy() for k in ("edge_action", "edge_n", "edge_q", "edge_p")]
         parts = [np.split(c, np.cumsum(n)[:-1]) for c in cols]
+        # nodes expanded with the uniform prior do not store P per edge: it is 1/nedge (the same float64 division)
+        uni = self.t["node_uniform"].index_select(0, root).cpu().numpy()
+        for t in range(self.B):
+            if uni[t] and n[t]:
+                parts[3][t] = np.full(n[t], np.float64(1.0) / np.float64(n[t]))
         return [tuple(col[t] for col in parts) for t in range(self.B)]
 
     def best_actions_device(self) -> torch.Tensor:
