@@ -219,6 +219,29 @@ __device__ __forceinline__ void expand_tree(const ExpandArgs &a, uint32_t *words
     const double uni = n > 0 ? __ddiv_rn(1.0, static_cast<double>(n)) : 0.0;
     int done_e = 0;                                        // edges already written (n exceeds kMaxIds only in theory)
     const int skip = incl - mine;                          // this lane's first position in id order
+    if (n <= kMaxIds) {
+        // the usual case: everything fits one sweep, the compaction loop is as short as it gets (it was 60 % of the
+        // kernel's instructions with the window test inside)
+        uint16_t *dst = ids + skip;
+        const int g0 = lane * rounds, g1 = min(g0 + rounds, nwords);
+        for (int g = g0; g < g1; ++g) {
+            uint32_t w = words[g];
+            const int base = g << 5;
+            while (w) {
+                *dst++ = static_cast<uint16_t>(base + __ffs(w) - 1);
+                w &= w - 1;
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const int id = ids[i];
+            const int e = e0 + i;
+            f.edge_action[e] = id; f.edge_child[e] = -1; f.edge_n[e] = 0.0; f.edge_q[e] = 0.0;
+            if (a.prior_dtype == 1) f.edge_p[e] = static_cast<double>(reinterpret_cast<const float *>(a.prior)[t * a.prior_stride + id]);
+            else if (a.prior_dtype == 2) f.edge_p[e] = reinterpret_cast<const double *>(a.prior)[t * a.prior_stride + id];
+        }
+        done_e = n;
+    }
     while (done_e < n) {
         int pos = skip;
         for (int j = 0; j < rounds; ++j) {
