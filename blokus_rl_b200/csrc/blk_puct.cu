@@ -25,6 +25,7 @@ namespace {
 
 constexpr uint32_t kAll = 0xffffffffu;
 constexpr int kWarpsPerBlock = 4;
+constexpr int kSelUnroll = 4;      // edges per lane whose N, Q (and P) loads are in flight together in puct_select_kernel
 constexpr int kMaxIds = 1024;      // legal ids compacted per sweep of puct_expand_kernel (20x20 positions have <= ~800)
 
 // A fused expansion (ExpandArgs::fuse_backup) cannot move the pool-slot counter itself -- warps of the same launch still
@@ -53,10 +54,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_select_kernel(blk_pu
         const double sq = __dsqrt_rn(__dadd_rn(s, (eps_fix || depth > 0) ? 1e-6 : 0.0));
         double best = -1.0e300;
         int besti = 0x7fffffff;
-        for (int i0 = lane; i0 < n; i0 += 128) {               // four edges per lane in flight (12 loads), then the arithmetic
-            double ep[4], en[4], eq[4];
+        for (int i0 = lane; i0 < n; i0 += 32 * kSelUnroll) {    // kSelUnroll edges per lane in flight, then the arithmetic
+            double ep[kSelUnroll], en[kSelUnroll], eq[kSelUnroll];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < kSelUnroll; ++k) {
                 const int i = i0 + 32 * k;
                 const bool in = i < n;
                 ep[k] = uniform ? pu : (in ? __ldg(f.edge_p + e0 + i) : 0.0);
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) puct_select_kernel(blk_pu
                 eq[k] = in ? __ldg(f.edge_q + e0 + i) : 0.0;
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < kSelUnroll; ++k) {
                 const int i = i0 + 32 * k;
                 const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c, ep[k]), sq), __dadd_rn(1.0, en[k]));
                 const double sc = __dadd_rn(eq[k], u);
