@@ -32,6 +32,10 @@
 extern "C" {
 #endif
 
+/* ABI history: 1 = first release of this round; 2 = blk_step_args grew `obs` (fused observation output) and `state_index`
+ * (step states out of a pool), blk_rollout_args grew `options`, BLK_OPT_WARP_KERNELS, blk_puct_forest grew `node_uniform`
+ * and a 6th counter, blk_puct_expand_args grew `fuse_backup`.  All additions are trailing fields: zero-initialised structs keep
+ * their version-1 meaning. */
 #define BLK_ABI_VERSION 2
 
 typedef enum {
