@@ -63,7 +63,8 @@ class GpuPuct:
                                              "step_action", "scores", "counters", "node_sum_n", "path_node", "node_uniform")])
         # a net needs the dense bool mask; the uniform prior only needs the legal ids, which the 8x smaller
         # bit-packed mask gives just as well
-        self.mask_fmt = "bits" if isinstance(self.evaluator, UniformEvaluator) else "bytes"
+        self.uniform = bool(getattr(self.evaluator, "uniform_prior", False))
+        self.mask_fmt = "bits" if self.uniform else "bytes"
         self.buf = engine.make_buffers(self.B, self.mask_fmt)
         # a net evaluator gets its input planes from the same launch that produces the new states and masks
         self.obs = (torch.empty((self.B, 2 * self.P, engine.board_size, engine.board_size), dtype=torch.float32, device=dev)
@@ -111,7 +112,10 @@ class GpuPuct:
         out = eng.step(self.pool, t["step_action"], out_states=self.stage, state_index=t["src_slot"], buffers=self.buf,
                        mask=self.mask_fmt, want_count=False, want_scores=False, obs=None if attach_only else self.obs)
         prior, pd, ps, value = None, 0, 0, None
-        if not attach_only and not isinstance(self.evaluator, UniformEvaluator):
+        if not attach_only and self.uniform:
+            v = self.evaluator.values(eng, self.stage)       # uniform prior: expanded as P = 1/n on the device
+            value = None if v is None else v.to(torch.float64).contiguous()
+        elif not attach_only:
             if self.obs is not None:
                 p, v = self.evaluator.evaluate(eng, self.stage, out.mask, obs=self.obs)
             else:

@@ -28,11 +28,17 @@ import torch
 
 # ------------------------------------------------------------------------------------------------
 # evaluators:  evaluate(engine, states int32 [m, SW], mask bool [m, A]) -> (p [m, A] float, v [m, P] float)
+#   An evaluator with ``uniform_prior = True`` also offers values(engine, states) -> v [m, P] or None (zeros): the device forest
+#   then expands with P = 1/n itself and never materialises the dense prior.
 #   An evaluator with ``wants_obs = True`` is also handed ``obs=`` (float32 [m, 2P, N, N]) when the caller already has
 #   it from the step kernel's fused observation output (GpuPuct), and computes it itself otherwise.
 # ------------------------------------------------------------------------------------------------
 class UniformEvaluator:
     graph_safe = True          # no host work: GpuPuct may capture it into a CUDA graph
+    uniform_prior = True       # prior = 1/n over the legal actions; values() is all GpuPuct needs (None = zeros)
+
+    def values(self, engine, states):
+        return None
 
     def evaluate(self, engine, states, mask):
         cnt = mask.sum(1, keepdim=True).clamp(min=1).to(torch.float64)
@@ -42,15 +48,19 @@ class UniformEvaluator:
 
 class RolloutEvaluator:
     """Uniform priors, value = mean 3/1/-1 vector over ``per_leaf`` uniform-random GPU playouts."""
+    uniform_prior = True       # GpuPuct asks only for values(): no dense [m, A] float64 prior is built per simulation
 
     def __init__(self, per_leaf: int = 32, seed: int = 0):
         self.per_leaf, self.seed, self._calls = per_leaf, seed, 0
 
-    def evaluate(self, engine, states, mask):
+    def values(self, engine, states):
         out = engine.rollout(states, self.per_leaf, seed=self.seed, rollout_id_base=self._calls)
         self._calls += states.shape[0] * self.per_leaf
+        return (out.value_sum / self.per_leaf).to(torch.float64)
+
+    def evaluate(self, engine, states, mask):
         cnt = mask.sum(1, keepdim=True).clamp(min=1).to(torch.float64)
-        return mask.to(torch.float64) / cnt, (out.value_sum / self.per_leaf).to(torch.float64)
+        return mask.to(torch.float64) / cnt, self.values(engine, states)
 
 
 class TorchNetEvaluator:
