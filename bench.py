@@ -156,6 +156,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: anything libraries print there while the bench runs (NCCL writes its
+    # "NCCL version ..." banner to stdout when NCCL_DEBUG is set) is sent to stderr; the real stdout comes back for the line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -305,7 +310,11 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": plies / secs, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{plies} plies of {N}x{N} {P}p random-legal play with full byte masks, one env per "
                                           f"host thread, {secs:.1f} s (oracle port, bit-parallel variant)"}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)                                   # teardown chatter, if any, stays off stdout too
     if world > 1:
         dist.destroy_process_group()
 
