@@ -3,7 +3,8 @@
 its random player and arena do per ply -- get_sample_move -> get_next_state -> get_valid_moves -> get_game_ended -- over this
 repo's colosseumrl shim on the CPU oracle.  The Python overheads the reference really pays are included (243 KB float64
 mask per call, string <-> id dictionaries); the engine under the shim is the restatement, not colosseumrl.
-Needs /root/reference (build container only).   python tools/ref_wrapper_cpu_rate.py [plies]"""
+Needs /root/reference (build container only).   python tools/ref_wrapper_cpu_rate.py [plies] [processes]
+With processes > 1 the same loop runs in that many processes at once, one env each ("all host cores")."""
 import os
 import sys
 import tempfile
@@ -17,6 +18,17 @@ from oracle_backend import OracleBackend
 from blokus_rl_b200 import colosseum_shim
 
 plies_wanted = int(sys.argv[1]) if len(sys.argv) > 1 else 600
+procs = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+if procs > 1:                                   # one env per process, all at once; every child prints its own rate
+    import subprocess
+    t0 = time.perf_counter()
+    kids = [subprocess.Popen([sys.executable, __file__, str(plies_wanted)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for _ in range(procs)]
+    outs = [k.communicate()[0] for k in kids]
+    for tag in ("20x20 4p", "7x7 2p"):
+        rates = [float(ln.split(" = ")[1].split(" plies/s")[0]) for o in outs for ln in o.splitlines() if ln.startswith(tag)]
+        print(f"{tag}: {procs} processes at once: {sum(rates):.0f} plies/s in total ({min(rates):.0f}..{max(rates):.0f} per process)")
+    sys.exit(0)
 for (N, P) in ((20, 4), (7, 2)):
     backend = OracleBackend(N, P)
     colosseum_shim.set_backend(backend)
