@@ -59,6 +59,37 @@ def test_generated_inc_is_current():
     before = inc.read_text()
     subprocess.check_call([sys.executable, str(root / "tools" / "gen_orient_inc.py")], stdout=subprocess.DEVNULL)
     assert inc.read_text() == before
+    small = root / "blokus_rl_b200" / "csrc" / "blk_small_fields.inc"          # bit-stream code of the small-board kernels
+    before = small.read_text()
+    subprocess.check_call([sys.executable, str(root / "tools" / "gen_small_inc.py")], stdout=subprocess.DEVNULL)
+    assert small.read_text() == before
+
+
+def test_small_board_bit_stream_matches_action_table():
+    """blk_small_fields.inc: the fields of every orientation, appended row by row, tile the action ids 0..A-1 exactly --
+    (half, shift) is anchor row y of a stride-8 bitboard, W the number of anchor columns, fill the bit inside the mask word."""
+    import re
+    from pathlib import Path
+    txt = (Path(__file__).resolve().parents[1] / "blokus_rl_b200" / "csrc" / "blk_small_fields.inc").read_text()
+    for n in (5, 6, 7):
+        sec = txt.split(f"#if BLK_SMALL_N == {n}\n")[1].split("#endif\n#endif")[0]
+        t = tables.action_table(n)
+        assert f"#define BLK_SMALL_A {t.num_actions}" in sec
+        bit, orient = 0, -1
+        for ln in sec.splitlines():
+            m = re.match(r"SM_ORIENT\((\d+), (\d+), (\d+),", ln)
+            if m:
+                orient, y = int(m.group(1)), 0
+                assert bit == t.orient_base[orient] and int(m.group(2)) == tables.orientations()[orient].piece
+                continue
+            m = re.match(r"SM_FIELD(_X)?\((\d), (\d+), (\d+), (\d+)", ln)
+            if m:
+                half, shift, w, fill = (int(m.group(k)) for k in (2, 3, 4, 5))
+                o = tables.orientations()[orient]
+                assert 4 * half + shift // 8 == y and shift % 8 == 0 and w == n - o.w + 1 and fill == bit % 32
+                assert (m.group(1) is not None) == (fill + w > 32)
+                bit, y = bit + w, y + 1
+        assert bit == t.num_actions
 
 
 def test_first_move_count_and_corners(oracle20, oracle7):
