@@ -12,15 +12,16 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .engine import BlokusEngine
+from ._lib import BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED
+from .engine import BlokusEngine, StepOut
 
 
 class StateHandle:
-    """Immutable env state: device words + lazily fetched host views."""
-    __slots__ = ("words", "host_words", "mask_dev", "_mask", "flags", "terminal", "scores", "_obs", "_board")
+    """Immutable env state: device words + the host copy of everything the step that produced it returned."""
+    __slots__ = ("words", "host_words", "ids", "_mask", "flags", "terminal", "scores", "_obs", "_board")
 
-    def __init__(self, words, host_words, mask_dev, flags, terminal, scores):
-        self.words, self.host_words, self.mask_dev = words, host_words, mask_dev
+    def __init__(self, words, host_words, ids, flags, terminal, scores):
+        self.words, self.host_words, self.ids = words, host_words, ids
         self.flags, self.terminal, self.scores = flags, terminal, scores
         self._mask = self._obs = self._board = None
 
@@ -31,27 +32,61 @@ class EngineBackend:
         self.eng = engine if engine is not None else BlokusEngine(board_size, num_players, score_rule, device)
         self.N, self.P, self.A = self.eng.board_size, self.eng.num_players, self.eng.num_actions
         self._meta = self.P * self.N + self.P
+        # Every output of a transition lands in ONE device buffer, so a transition costs one launch and ONE device-to-host
+        # copy (the reference's search makes 25-200 of them per move, blokus_rl/alphazero/mcts.py:47-71):
+        #   state words | terminal f32[P] | scores i16[P] | legal_count i32 | flags u8 | legal ids u16[max_legal]
+        # The mask travels in the sparse BLK_MASK_INDICES form (~350 B instead of 30 KB).
+        a16 = lambda x: (x + 15) & ~15
+        self._o_term = a16(4 * self.eng.state_words)
+        self._o_score = self._o_term + 16
+        self._o_count = self._o_score + 16
+        self._o_flags = self._o_count + 4
+        self._o_ids = a16(self._o_flags + 1)
+        self._pack_bytes = self._o_ids + 2 * self.eng.max_legal
 
     # ---- construction ------------------------------------------------------------------------------
-    def _finish(self, out) -> StateHandle:
-        host = out.states.cpu().numpy().view(np.uint32)[0].copy()      # one small D2H + sync
-        return StateHandle(out.states, host, out.mask, int(out.flags.item()), out.terminal.cpu().numpy()[0],
-                           out.scores.cpu().numpy()[0])
+    def _views(self, pack: torch.Tensor):
+        P, SW = self.P, self.eng.state_words
+        words = pack[: 4 * SW].view(torch.int32).view(1, SW)
+        bufs = StepOut(None, None,
+                       pack[self._o_count: self._o_count + 4].view(torch.int32),
+                       pack[self._o_term: self._o_term + 4 * P].view(torch.float32).view(1, P),
+                       pack[self._o_flags: self._o_flags + 1],
+                       pack[self._o_score: self._o_score + 2 * P].view(torch.int16).view(1, P), None)
+        ids = pack[self._o_ids:].view(torch.int16).view(1, self.eng.max_legal)
+        return words, bufs, ids
+
+    def _transition(self, src: torch.Tensor, action: torch.Tensor | None) -> StateHandle:
+        """One ``blk_step`` launch (n = 1) whose outputs all land in one buffer, then one D2H copy of it."""
+        pack = torch.empty(self._pack_bytes, dtype=torch.uint8, device=self.eng.device)
+        words, bufs, ids = self._views(pack)
+        if action is None:
+            words.copy_(src)
+            src = words
+        self.eng.step(src, action, out_states=words, mask=ids, buffers=bufs)
+        host = pack.cpu().numpy()                                          # the one synchronising copy
+        flags = int(host[self._o_flags])
+        n = int(host[self._o_count: self._o_count + 4].view(np.int32)[0])
+        if flags & BLK_FLAG_TRUNCATED:                                     # more legal moves than the id row holds
+            m = self.eng.step(words, None, mask="bytes", want_count=False, want_terminal=False, want_scores=False).mask
+            hids = np.flatnonzero(m[0].cpu().numpy()).astype(np.int64)
+        else:
+            hids = host[self._o_ids: self._o_ids + 2 * n].view(np.uint16).astype(np.int64)
+        return StateHandle(words, host[: 4 * self.eng.state_words].view(np.uint32).copy(), hids, flags,
+                           host[self._o_term: self._o_term + 4 * self.P].view(np.float32).copy(),
+                           host[self._o_score: self._o_score + 2 * self.P].view(np.int16).copy())
 
     def new_state(self) -> StateHandle:
-        s = self.eng.new_states(1)
-        return self._finish(self.eng.step(s, None, mask="bytes"))
+        return self._transition(self.eng.new_states(1), None)
 
     def from_words(self, words: np.ndarray) -> StateHandle:
         s = torch.from_numpy(np.ascontiguousarray(words, np.uint32).view(np.int32).reshape(1, -1)).to(self.eng.device)
-        return self._finish(self.eng.step(s, None, mask="bytes"))
+        return self._transition(s, None)
 
     def next_state(self, h: StateHandle, action_id: int) -> StateHandle:
-        act = torch.tensor([int(action_id)], dtype=torch.int32, device=self.eng.device)
-        dst = torch.empty_like(h.words)
-        out = self.eng.step(h.words, act, out_states=dst, mask="bytes")
-        nh = self._finish(out)
-        if nh.flags & 2:
+        act = torch.tensor([int(action_id)], dtype=torch.int32).to(self.eng.device, non_blocking=True)
+        nh = self._transition(h.words, act)
+        if nh.flags & BLK_FLAG_ILLEGAL:
             raise ValueError(f"illegal action {action_id} for player {self.mover(h)}")
         return nh
 
@@ -67,11 +102,12 @@ class EngineBackend:
 
     def legal_mask(self, h: StateHandle) -> np.ndarray:
         if h._mask is None:
-            h._mask = h.mask_dev[0].cpu().numpy().astype(np.uint8)
+            h._mask = np.zeros(self.A, np.uint8)
+            h._mask[h.ids] = 1
         return h._mask
 
     def legal_ids(self, h: StateHandle) -> np.ndarray:
-        return np.flatnonzero(self.legal_mask(h))
+        return h.ids
 
     def winners(self, h: StateHandle) -> list[int]:
         if not self.done(h):

@@ -12,7 +12,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "blk_kernels.cuh"
@@ -54,6 +56,20 @@ int fail(int code, const std::string &msg) {
     g_err = msg;
     return code;
 }
+// Entry points run on the engine's device and leave the caller's current device as they found it (a process that
+// drives engines on several GPUs, or torch with another current device, must not be switched under its feet).
+struct DeviceGuard {
+    int prev = -1, dev;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int d) : dev(d) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+
 #define CUDA_TRY(expr)                                                                              \
     do {                                                                                            \
         cudaError_t e_ = (expr);                                                                    \
@@ -214,8 +230,14 @@ struct blk_engine {
     Geometry g;
     TableLayout t;
     unsigned char *d_tables = nullptr;
-    unsigned long long *d_queue = nullptr;   // kQueueSlots x {ticket, finished}; launch i uses slot i % kQueueSlots
-    unsigned launch_seq = 0;
+    // Work-queue counters: kQueueSlots x {ticket, finished}, self-resetting at the end of every launch.  Two launches may
+    // share a slot only if they cannot overlap, so a slot belongs to ONE stream (launches of a stream run in order) or
+    // to ONE stream capture (a captured launch keeps its slot for every replay of the graph, wherever that is
+    // launched; eager launches never get that slot).  `mu` guards the map: entry points may be called from several
+    // host threads.
+    unsigned long long *d_queue = nullptr;
+    std::mutex mu;
+    std::unordered_map<unsigned long long, int> slot_of;
     int sm_count = 0;
     int step_smem = 0, roll_smem = 0;
     int step_blocks_per_sm = 0, rollout_blocks_per_sm = 0;
@@ -349,6 +371,34 @@ int build_tables(blk_engine *h) {
     return BLK_OK;
 }
 
+// The work-queue slot of a launch on `st` (see blk_engine::d_queue).
+int queue_slot(blk_engine *h, cudaStream_t st, unsigned long long **out) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    unsigned long long cap_id = 0;
+    if (cudaStreamGetCaptureInfo(st, &cs, &cap_id) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BLK_ERR_CUDA, "cudaStreamGetCaptureInfo failed (bad stream handle?)");
+    }
+    // keys: streams are pointers (low bits 0, or the small special handles 0/1/2); captures get an odd key that mixes
+    // the capture id with the stream, so forked capture streams of one capture do not share a slot either
+    unsigned long long key = static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(st)) << 1;
+    if (cs == cudaStreamCaptureStatusActive) key = ((cap_id * 0x9E3779B97F4A7C15ULL) ^ key) | 1ULL;
+    else if (cs != cudaStreamCaptureStatusNone) return fail(BLK_ERR_CUDA, "stream capture was invalidated");
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->slot_of.find(key);
+    int slot;
+    if (it != h->slot_of.end()) {
+        slot = it->second;
+    } else {
+        if (static_cast<int>(h->slot_of.size()) >= kQueueSlots)
+            return fail(BLK_ERR_ARG, "too many distinct streams / graph captures on one engine (work-queue slots exhausted)");
+        slot = static_cast<int>(h->slot_of.size());
+        h->slot_of.emplace(key, slot);
+    }
+    *out = h->d_queue + 2 * slot;
+    return BLK_OK;
+}
+
 int grid_for(int64_t units, int per_block, int sm_count, int blocks_per_sm) {
     const int64_t need = (units + per_block - 1) / per_block;
     const int64_t cap = static_cast<int64_t>(sm_count) * blocks_per_sm;
@@ -372,7 +422,8 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(BLK_ERR_NODEV, "no CUDA device: this engine has no CPU fallback");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(BLK_ERR_ARG, "device ordinal out of range");
-    CUDA_TRY(cudaSetDevice(cfg->device));
+    DeviceGuard guard(cfg->device);
+    CUDA_TRY(guard.err);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) return fail(BLK_ERR_NODEV, "device is not sm_100 (B200); kernels are built for sm_100a only");
@@ -447,6 +498,7 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
 
 void blk_destroy(blk_engine *h) {
     if (!h) return;
+    DeviceGuard guard(h->cfg.device);
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_queue) cudaFree(h->d_queue);
     if (h->d_small) cudaFree(h->d_small);
@@ -481,7 +533,8 @@ int blk_action_to_cells(const blk_engine *h, int32_t action, int32_t meta[4], ui
 int blk_reset(blk_engine *h, uint32_t *state, int64_t n, void *stream) {
     if (!h || (!state && n > 0) || n < 0) return fail(BLK_ERR_ARG, "bad argument to blk_reset");
     if (n == 0) return BLK_OK;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(guard.err);
     const int64_t words = n * h->g.sw;
     reset_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(state, n, h->g);
     CUDA_TRY(cudaGetLastError());
@@ -505,10 +558,10 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
     if (args->obs && (reinterpret_cast<uintptr_t>(args->obs) & 15) != 0) return fail(BLK_ERR_ARG, "obs must be 16 B aligned");
     if (args->state_index && (!args->state_out || args->state_out == args->state_in))
         return fail(BLK_ERR_ARG, "state_index needs a separate state_out");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(guard.err);
     KParams kp;
     kp.a = *args; kp.tables = h->d_tables; kp.t = h->t; kp.g = h->g;
-    kp.queue = h->d_queue + 2 * (h->launch_seq++ % kQueueSlots);
     const int grid = grid_for(args->n, kWarps, h->sm_count, h->step_blocks_per_sm);
     int variant = args->mask_format;                  // 0 none, 1 bits, 2 bytes (vector stores), 3 bytes (unaligned buffer), 4 ids
     if (variant == BLK_MASK_INDICES) variant = 4;
@@ -530,6 +583,10 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
         CUDA_TRY(cudaGetLastError());
         return BLK_OK;
     }
+    {
+        const int rc = queue_slot(h, static_cast<cudaStream_t>(stream), &kp.queue);
+        if (rc != BLK_OK) return rc;
+    }
     h->ks.step[variant][args->next_action != nullptr ? 1 : 0]<<<grid, kWarps * 32, h->step_smem, static_cast<cudaStream_t>(stream)>>>(kp);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
@@ -538,7 +595,8 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
 int blk_observe(blk_engine *h, const uint32_t *state, float *obs, int64_t n, void *stream) {
     if (!h || n < 0 || (n > 0 && (!state || !obs))) return fail(BLK_ERR_ARG, "bad argument to blk_observe");
     if (n == 0) return BLK_OK;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(guard.err);
     const int64_t elems = n * 2 * h->g.P * h->g.N * h->g.N;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool aligned = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
@@ -560,7 +618,8 @@ int blk_observe(blk_engine *h, const uint32_t *state, float *obs, int64_t n, voi
 int blk_board_contents(blk_engine *h, const uint32_t *state, uint8_t *board, int64_t n, void *stream) {
     if (!h || n < 0 || (n > 0 && (!state || !board))) return fail(BLK_ERR_ARG, "bad argument to blk_board_contents");
     if (n == 0) return BLK_OK;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(guard.err);
     const int64_t elems = n * h->g.N * h->g.N;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int wgrid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(h->sm_count) * 8));
@@ -576,7 +635,8 @@ int blk_game_ended(blk_engine *h, const uint32_t *state, uint8_t *flags, float *
                    void *stream) {
     if (!h || n < 0 || (n > 0 && !state)) return fail(BLK_ERR_ARG, "bad argument to blk_game_ended");
     if (n == 0) return BLK_OK;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(guard.err);
     ended_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(state, flags, terminal, scores, n, h->g);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
@@ -589,7 +649,8 @@ int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream) {
     if (!args->roots) return fail(BLK_ERR_ARG, "roots are required");
     if (args->stop_player < -1 || args->stop_player >= h->g.P) return fail(BLK_ERR_ARG, "stop_player out of range");
     if (args->action_log && args->log_stride < 4 * kPieces + 1) return fail(BLK_ERR_ARG, "log_stride must be >= 85");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(guard.err);
     if (h->small && !(args->options & BLK_OPT_WARP_KERNELS)) {
         // N <= 7: one playout per thread on 64-bit bitboards (blk_small.cu); identical games, ~an order of magnitude faster
         SmallRollParams sp;
@@ -603,7 +664,10 @@ int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream) {
     }
     RParams rp;
     rp.a = *args; rp.tables = h->d_tables; rp.t = h->t; rp.g = h->g;
-    rp.queue = h->d_queue + 2 * (h->launch_seq++ % kQueueSlots);
+    {
+        const int rc = queue_slot(h, static_cast<cudaStream_t>(stream), &rp.queue);
+        if (rc != BLK_OK) return rc;
+    }
     const int grid = grid_for(args->n_roots * args->per_root, kRollWarps, h->sm_count, h->rollout_blocks_per_sm);
     h->ks.rollout<<<grid, kRollWarps * 32, h->roll_smem, static_cast<cudaStream_t>(stream)>>>(rp);
     CUDA_TRY(cudaGetLastError());

@@ -55,7 +55,7 @@ constexpr uint32_t kAllLanes = 0xffffffffu;
 #ifndef BLK_ROW_ALIGN
 #define BLK_ROW_ALIGN 128   // byte-mask rows start on 128 B lines: every 512 B warp store is line-aligned (+3.5 % measured)
 #endif
-constexpr int kQueueSlots = 64;   // work-queue counters for up to 64 launches of one engine in flight at once
+constexpr int kQueueSlots = 4096;   // work-queue counter pairs: one per stream / per graph capture that ever launched on the engine
 constexpr int kEmitUnroll = BLK_EMIT_UNROLL;   // passes of the emit loop unrolled together (ILP vs I-cache)
 constexpr int kOffLut = 0, kOffWdesc = 2048;   // fixed offsets inside the table blob (see TableLayout)
 

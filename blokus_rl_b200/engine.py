@@ -192,7 +192,13 @@ class BlokusEngine:
             if not want:
                 return None
             t = getattr(b, name, None) if b is not None else None
-            return t if t is not None else torch.empty(shape, dtype=dtype, device=dev)
+            if t is None:
+                return torch.empty(shape, dtype=dtype, device=dev)
+            # a reused buffer made for a smaller batch would be written past its end by the kernel
+            if t.dtype != dtype or t.device != dev or not t.is_contiguous() or t.dim() != len(shape) \
+                    or t.shape[0] < n or tuple(t.shape[1:]) != tuple(shape[1:]):
+                raise ValueError(f"buffers.{name} must be a contiguous {dtype} tensor of shape >= {tuple(shape)} on {dev}")
+            return t
 
         P = self.num_players
         legal_count = buf("legal_count", (n,), torch.int32, want_count)
@@ -208,7 +214,7 @@ class BlokusEngine:
         elif obs is False:
             obs = None
         if obs is not None and (obs.dtype != torch.float32 or obs.device != dev or not obs.is_contiguous()
-                                or obs.numel() != n * 2 * P * N * N):
+                                or obs.numel() < n * 2 * P * N * N):
             raise ValueError("obs must be a contiguous float32 [n, 2P, N, N] CUDA tensor")
         args = _lib.BlkStepArgs(
             n, states.data_ptr(), out_states.data_ptr(), None if actions is None else actions.data_ptr(),
@@ -284,9 +290,12 @@ class BlokusEngine:
         plies = torch.empty((n, per_root), dtype=torch.int32, device=dev)
         log_stride = 88
         log = torch.empty((n, per_root, log_stride), dtype=torch.int16, device=dev) if log_actions else None
-        if out_states is not None and (out_states.dtype != torch.int32 or not out_states.is_contiguous()
-                                       or out_states.numel() != total * self.state_words):
-            raise ValueError("out_states must be a contiguous int32 [n * per_root, state_words] tensor")
+        if out_states is not None:
+            if out_states.dtype != torch.int32 or not out_states.is_contiguous() or out_states.device != dev \
+                    or out_states.numel() != total * self.state_words:
+                raise ValueError(f"out_states must be a contiguous int32 [n * per_root, state_words] tensor on {dev}")
+            if per_root > 1 and out_states.untyped_storage().data_ptr() == roots.untyped_storage().data_ptr():
+                raise ValueError("out_states may alias roots only when per_root == 1 (playouts of one root would overwrite it)")
         args = _lib.BlkRolloutArgs(n, roots.data_ptr(), per_root, seed & 0xFFFFFFFFFFFFFFFF, rollout_id_base & 0xFFFFFFFF,
                                    final_scores.data_ptr(), winners.data_ptr(), value_sum.data_ptr(),
                                    None if log is None else log.data_ptr(), log_stride, plies.data_ptr(),

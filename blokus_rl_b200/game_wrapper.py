@@ -61,6 +61,11 @@ class BlokusGameWrapper:
 
     # ---- masks / observations (blokus_wrapper.py:108-162) ------------------------------------------------
     def get_valid_moves(self, current_state, current_player=-1):
+        # the reference hands `current_player` to env.valid_actions (blokus_wrapper.py:121-124); every call site passes the
+        # state's own side to move (or -1), and the engine only ever evaluates that player
+        if current_player not in (-1, self.backend.mover(current_state)):
+            raise ValueError(f"get_valid_moves: player {current_player} is not the side to move "
+                             f"({self.backend.mover(current_state)}) of this state")
         return self.backend.legal_mask(current_state).astype(np.float64)
 
     def get_observation(self, state, player):

@@ -31,11 +31,23 @@ class GpuPuct:
         self.B, self.P, self.A = num_trees, engine.num_players, engine.num_actions
         self._lib = _lib.load()
         dev = engine.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
         self.node_cap = num_trees * (max_simulations + 2)
         self.edge_cap = self.node_cap * mean_edges_per_node
         self.max_depth = max_depth
-        i32 = dict(dtype=torch.int32, device=dev)
-        f64 = dict(dtype=torch.float64, device=dev)
+        # Memory: nodes 4 * state_words + 29 + 8 P bytes each (the state pool dominates), edges 32 B each (24 B with a
+        # uniform-prior evaluator, which stores no per-edge P).  The C ABI carries capacities as int32.
+        if self.node_cap >= 2 ** 31 or self.edge_cap >= 2 ** 31:
+            raise ValueError(f"GpuPuct: num_trees * (max_simulations + 2) * mean_edges_per_node = {self.edge_cap} edges does "
+                             "not fit the forest's int32 indices; search fewer trees per forest or fewer simulations")
+        self.uniform = bool(getattr(self.evaluator, "uniform_prior", False))
+        edge_bytes = self.edge_cap * (24 if self.uniform else 32)
+        free = torch.cuda.mem_get_info(dev)[0] if dev.type == "cuda" else edge_bytes * 4
+        if edge_bytes + self.node_cap * 4 * engine.state_words > 0.9 * free:
+            raise ValueError(f"GpuPuct: the forest needs {(edge_bytes + self.node_cap * 4 * engine.state_words) / 2**30:.1f} GiB "
+                             f"({self.edge_cap} edges, {self.node_cap} nodes) but {free / 2**30:.1f} GiB are free; lower "
+                             "num_trees, max_simulations or mean_edges_per_node")
         t = self.t = {
             "node_edge0": torch.empty(self.node_cap, **i32), "node_nedge": torch.empty(self.node_cap, **i32),
             "node_state": torch.empty(self.node_cap, **i32),
@@ -44,7 +56,7 @@ class GpuPuct:
             "node_term_value": torch.empty((self.node_cap, self.P), **f64),
             "edge_action": torch.empty(self.edge_cap, **i32), "edge_child": torch.empty(self.edge_cap, **i32),
             "edge_n": torch.empty(self.edge_cap, **f64), "edge_q": torch.empty(self.edge_cap, **f64),
-            "edge_p": torch.empty(self.edge_cap, **f64),
+            "edge_p": torch.empty(1 if self.uniform else self.edge_cap, **f64),   # uniform prior: P = 1/n, never stored
             "root": torch.empty(self.B, **i32), "path": torch.empty((self.B, max_depth), **i32),
             "path_len": torch.zeros(self.B, **i32), "status": torch.zeros(self.B, **i32),
             "leaf_node": torch.zeros(self.B, **i32), "leaf_edge": torch.zeros(self.B, **i32),
@@ -63,7 +75,6 @@ class GpuPuct:
                                              "step_action", "scores", "counters", "node_sum_n", "path_node", "node_uniform")])
         # a net needs the dense bool mask; the uniform prior only needs the legal ids, which the 8x smaller
         # bit-packed mask gives just as well
-        self.uniform = bool(getattr(self.evaluator, "uniform_prior", False))
         self.mask_fmt = "bits" if self.uniform else "bytes"
         self.buf = engine.make_buffers(self.B, self.mask_fmt)
         # a net evaluator gets its input planes from the same launch that produces the new states and masks
@@ -192,7 +203,8 @@ class GpuPuct:
         n = np.where(e0 < 0, 0, n)
         idx = np.concatenate([np.arange(a, a + b) for a, b in zip(e0, n)]) if n.sum() else np.zeros(0, np.int64)
         di = torch.as_tensor(idx, device=root.device, dtype=torch.long)
-        cols = [self.t[k].index_select(0, di).cpu().numpy() for k in ("edge_action", "edge_n", "edge_q", "edge_p")]
+        cols = [self.t[k].index_select(0, di).cpu().numpy() for k in ("edge_action", "edge_n", "edge_q")]
+        cols.append(np.zeros(len(idx)) if self.uniform else self.t["edge_p"].index_select(0, di).cpu().numpy())
         parts = [np.split(c, np.cumsum(n)[:-1]) for c in cols]
         # nodes expanded with the uniform prior do not store P per edge: it is 1/nedge (the same float64 division)
         uni = self.t["node_uniform"].index_select(0, root).cpu().numpy()

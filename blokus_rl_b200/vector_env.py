@@ -4,7 +4,7 @@ What the reference's PPO loop calls (``blokus_rl/ppo/trainer.py:36-38, 68, 111, 
 ``ppo/agent.py:112-114, 205-206`` and ``ppo/memory.py:18-25``):
 
     obs, info = envs.reset()
-    envs.get_attr("ai_possible_indexes")           # list[list[int]]: the agent's legal action ids per env
+    envs.get_attr("ai_possible_indexes")           # per env: the agent's legal action ids
     obs, reward, terminated, truncated, info = envs.step(actions)        # np int actions
     info["final_info"][i]["episode"]["r" | "l"]    # gymnasium-0.29 autoreset episode statistics
     envs.single_observation_space.shape, envs.single_action_space.n / .shape, envs.close()
@@ -15,14 +15,19 @@ ends, then +1 win / 0 draw / -1 loss for the agent.  Observation: the ``[N, N]``
 1..P colour), which is what ``CnnAgent`` unsqueezes to one channel (``ppo/agent.py:96-99, 112-113``).
 
 All envs live on the GPU; opponents are stepped by the engine's on-device Philox sampler, so one ``step`` is
-at most P kernel launches regardless of ``num_envs``.  GPU-native callers can skip the NumPy surface entirely:
-``step_device`` takes/returns CUDA tensors and ``action_mask`` is the bool ``[num_envs, A]`` tensor that
-``FilterLegalMoves`` (``ppo/agent.py:33-42``) would otherwise rebuild from index lists.
+a fixed handful of kernel launches regardless of ``num_envs``.  The NumPy surface moves only what the caller
+reads: per step ONE pinned staging buffer comes back (board cells, rewards, done flags, and the agent's legal ids
+in the sparse ``BLK_MASK_INDICES`` form -- a few hundred bytes per env instead of the 30 KB dense mask).
+GPU-native callers skip the NumPy surface entirely: ``step_device`` takes/returns CUDA tensors and ``action_mask``
+is the bool ``[num_envs, A]`` tensor that ``FilterLegalMoves`` (``ppo/agent.py:33-42``) would otherwise rebuild
+from index lists (it is produced on first use after a step).
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
+
+from ._lib import BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED
 
 
 class _Box:
@@ -52,27 +57,67 @@ class BlokusVectorEnv:
         self.action_space = _Box((num_envs,), np.int64, 0, self.A - 1)
         self.seed = seed
         self._meta = self.P * self.N + self.P
+        dev = engine.device
         self.states = None
-        self.action_mask = None            # bool [num_envs, A] on the device: the agent's legal actions
-        self._ep_len = torch.zeros(num_envs, dtype=torch.int64, device=engine.device)
-        self._ep_ret = torch.zeros(num_envs, dtype=torch.float32, device=engine.device)
+        self._next = torch.empty((num_envs, engine.state_words), dtype=torch.int32, device=dev)   # step target (commit on success)
+        self._fresh = engine.new_states(num_envs)
+        self._mask = None                  # dense bool mask of the current states, built on demand
+        self._ep_len = torch.zeros(num_envs, dtype=torch.int64, device=dev)
+        self._ep_ret = torch.zeros(num_envs, dtype=torch.float32, device=dev)
         self._epoch = 0
+        # sparse legal ids of the agent: row width grows when a position has more legal moves than fit
+        self._idx_stride = 128 if self.N <= 7 else 512
+        self._alloc_idx()
+        self._ids_host = None              # (counts, ids) of the current states on the host, filled on demand
+        self._h_board, self._h_reward = self._host((num_envs, self.N, self.N), torch.uint8), self._host(num_envs, torch.float32)
+        self._h_done = self._host(num_envs, torch.bool)
+
+    def _alloc_idx(self):
+        E, dev = self.num_envs, self.eng.device
+        self._idx = torch.empty((E, self._idx_stride), dtype=torch.int16, device=dev)
+        self._cnt = torch.empty(E, dtype=torch.int32, device=dev)
+        self._idx_flags = torch.empty(E, dtype=torch.uint8, device=dev)
+        self._h_idx, self._h_cnt = self._host((E, self._idx_stride), torch.int16), self._host(E, torch.int32)
+        self._h_idx_flags = self._host(E, torch.uint8)
+
+    def _host(self, shape, dtype):
+        # pinned staging memory (the CPU stand-in engine of the host-logic tests has none)
+        return torch.empty(shape, dtype=dtype, pin_memory=self.eng.device.type == "cuda")
 
     # ---- helpers ----------------------------------------------------------------------------------------
-    def _mover(self):
-        return (self.states[:, self._meta] & 15).long()
-
-    def _done(self):
-        return ((self.states[:, self._meta] >> 4) & 1).bool()
+    def _sync(self):
+        if self.eng.device.type == "cuda":
+            torch.cuda.current_stream(self.eng.device).synchronize()
 
     def _play_opponents(self):
         """Random bots move (one rollout launch, no host sync) until it is the agent's turn or the game is over."""
         self._epoch += 1
         self.eng.rollout(self.states, 1, seed=self.seed + self._epoch, stop_player=self.agent, out_states=self.states)
 
-    def _refresh_mask(self):
-        self.action_mask = self.eng.step(self.states, None, mask="bytes", want_count=False, want_terminal=False,
-                                         want_scores=False).mask
+    @property
+    def action_mask(self) -> torch.Tensor:
+        """bool [num_envs, A] on the device: the agent's legal actions in the current states."""
+        if self._mask is None:
+            self._mask = self.eng.step(self.states, None, mask="bytes", want_count=False, want_terminal=False,
+                                       want_scores=False).mask
+        return self._mask
+
+    def _launch_ids(self):
+        """Legal ids of the current states (sparse form) -> pinned host buffers; the caller synchronises."""
+        self.eng.step(self.states, None, mask=self._idx, want_terminal=False, want_scores=False,
+                      buffers=_Bufs(self._cnt, self._idx_flags))
+        self._h_idx.copy_(self._idx, non_blocking=True)
+        self._h_cnt.copy_(self._cnt, non_blocking=True)
+        self._h_idx_flags.copy_(self._idx_flags, non_blocking=True)
+
+    def _collect_ids(self):
+        """After a synchronise: (counts, ids) on the host; widens the id rows and retries when a row was truncated."""
+        while (self._h_idx_flags.numpy() & BLK_FLAG_TRUNCATED).any():
+            self._idx_stride *= 2
+            self._alloc_idx()
+            self._launch_ids()
+            self._sync()
+        self._ids_host = (self._h_cnt.numpy(), self._h_idx.numpy().view(np.uint16))
 
     def _obs(self):
         return self.eng.board_contents(self.states)
@@ -86,19 +131,22 @@ class BlokusVectorEnv:
         self._ep_ret.zero_()
         if self.agent != 0:
             self._play_opponents()
-        self._refresh_mask()
+        self._mask = self._ids_host = None
         return self._obs().cpu().numpy().astype(np.float32), {}
 
     def step_device(self, actions: torch.Tensor, check: bool = True):
         """Device-side step: int32 CUDA actions in; (obs uint8 [E,N,N], reward f32 [E], terminated bool [E],
         (episode returns, episode lengths, final observations) for the envs that finished) out, all on the
-        device.  With ``check=False`` nothing synchronises with the host (illegal actions then leave their env
-        unchanged, as ``blk_step`` defines)."""
+        device.  With ``check=True`` the env only advances when every action is legal (an illegal action raises
+        and leaves ALL envs as they were); with ``check=False`` nothing synchronises with the host and an illegal
+        action leaves just its own env unchanged, as ``blk_step`` defines."""
         eng = self.eng
-        out = eng.step(self.states, actions.to(torch.int32).contiguous(), mask=None, want_count=False,
-                       want_terminal=False, want_scores=False)
-        if check and bool((out.flags & 2).any()):
+        out = eng.step(self.states, actions.to(torch.int32).contiguous(), out_states=self._next, mask=None,
+                       want_count=False, want_terminal=False, want_scores=False)
+        if check and bool((out.flags & BLK_FLAG_ILLEGAL).any()):
             raise ValueError("illegal action passed to BlokusVectorEnv.step")
+        self.states, self._next = self._next, self.states              # commit
+        self._mask = self._ids_host = None
         self._play_opponents()
         flags, term, _ = eng.game_ended(self.states)
         done = (flags & 1).bool()
@@ -109,19 +157,24 @@ class BlokusVectorEnv:
         fin_ret, fin_len = self._ep_ret.clone(), self._ep_len.clone()
         final_obs = self._obs()
         # gymnasium-0.29 autoreset: finished envs restart at once and return the NEW episode's first observation
-        fresh = eng.new_states(self.num_envs)
-        self.states = torch.where(done[:, None], fresh, self.states).contiguous()
+        self.states = torch.where(done[:, None], self._fresh, self.states)
         self._ep_len = torch.where(done, torch.zeros_like(self._ep_len), self._ep_len)
         self._ep_ret = torch.where(done, torch.zeros_like(self._ep_ret), self._ep_ret)
         if self.agent != 0:
             self._play_opponents()
-        self._refresh_mask()
         return self._obs(), reward, done, (fin_ret, fin_len, final_obs)
 
     def step(self, actions):
-        acts = torch.as_tensor(np.asarray(actions), dtype=torch.int32, device=self.eng.device)
+        acts = torch.as_tensor(np.asarray(actions), dtype=torch.int32).to(self.eng.device, non_blocking=True)
         obs, reward, done, (fin_ret, fin_len, final_obs) = self.step_device(acts)
-        done_h = done.cpu().numpy()
+        # one round trip: board cells, rewards, done flags and the agent's next legal ids travel together
+        self._h_board.copy_(obs, non_blocking=True)
+        self._h_reward.copy_(reward, non_blocking=True)
+        self._h_done.copy_(done, non_blocking=True)
+        self._launch_ids()
+        self._sync()
+        self._collect_ids()
+        done_h = self._h_done.numpy().copy()
         info = {}
         if done_h.any():
             r, l = fin_ret.cpu().numpy(), fin_len.cpu().numpy()
@@ -131,15 +184,34 @@ class BlokusVectorEnv:
             info["final_observation"] = np.array([fo[i] if done_h[i] else None for i in range(self.num_envs)],
                                                  dtype=object)
             info["_final_info"] = done_h.copy()
-        return (obs.cpu().numpy().astype(np.float32), reward.cpu().numpy(), done_h,
+        return (self._h_board.numpy().astype(np.float32), self._h_reward.numpy().copy(), done_h,
                 np.zeros(self.num_envs, dtype=bool), info)
 
+    def legal_id_arrays(self):
+        """The agent's legal action ids per env as int64 arrays (views of one flat array): what
+        ``mask[i, possible_move] = 1`` indexes with (ppo/agent.py:36-37), without building Python lists."""
+        if self._ids_host is None:
+            self._launch_ids()
+            self._sync()
+            self._collect_ids()
+        cnt, ids = self._ids_host
+        keep = np.arange(ids.shape[1], dtype=np.int32)[None, :] < cnt[:, None]
+        return ids[keep].astype(np.int64), cnt
+
     def get_attr(self, name: str):
-        if name == "ai_possible_indexes":                # ppo/trainer.py:385
-            nz = torch.nonzero(self.action_mask).cpu().numpy()
-            splits = np.searchsorted(nz[:, 0], np.arange(self.num_envs + 1))
-            return [nz[splits[i]: splits[i + 1], 1].tolist() for i in range(self.num_envs)]
+        if name == "ai_possible_indexes":                # ppo/trainer.py:385 -> list[list[int]]
+            flat, cnt = self.legal_id_arrays()
+            flat, ends = flat.tolist(), np.cumsum(cnt).tolist()
+            return [flat[a:b] for a, b in zip([0] + ends[:-1], ends)]
         return [getattr(self, name)] * self.num_envs
 
     def close(self):
         self.states = None
+
+
+class _Bufs:
+    """The two per-step outputs the sparse-mask launch needs, in the shape ``BlokusEngine.step(buffers=...)`` reads."""
+    mask_raw = terminal = scores = next_action = obs = None
+
+    def __init__(self, legal_count, flags):
+        self.legal_count, self.flags = legal_count, flags

@@ -12,7 +12,10 @@
  *  - the caller (PyTorch) owns every device buffer; the engine owns only its constant tables.
  *  - all work is enqueued asynchronously on the cudaStream_t passed as `void* stream` (NULL = legacy
  *    default stream); nothing synchronises.
- *  - one engine handle per process and device; a handle is not thread-safe.
+ *  - an engine handle belongs to one device; its entry points restore the caller's current CUDA device before they
+ *    return and may be called from several host threads.  Launches on different streams may overlap; a launch captured
+ *    into a CUDA graph keeps working for every replay of that graph (do not run two instantiations of the SAME
+ *    captured graph concurrently).
  *  - there is no CPU fallback: a missing/failed CUDA device is an error.
  *
  * State format (uint32 words per env, `state_words` = P*N + P + 4; 88 words = 352 B at 20x20/4p):

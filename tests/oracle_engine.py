@@ -72,18 +72,25 @@ class OracleEngine:
         mt = None
         is_t = isinstance(mask, torch.Tensor)
         if mask == "indices" or (is_t and mask.dtype == torch.int16):
-            ids = np.zeros((n, self.max_legal), np.int16)
+            width = mask.shape[1] if is_t else self.max_legal
+            ids = np.zeros((n, width), np.int16)
             for i in range(n):
                 nz = np.flatnonzero(m[i])
-                if len(nz) > self.max_legal:
+                if len(nz) > width:
                     flags[i] |= 4
-                nz = nz[: self.max_legal]
+                nz = nz[:width]
                 ids[i, : len(nz)] = nz.astype(np.uint16).view(np.int16)
             mt = torch.from_numpy(ids)
+            if is_t:                                   # like the engine: the caller's buffer is written in place
+                mask.copy_(mt)
+                mt = mask
         elif mask == "bits" or (is_t and mask.dtype == torch.int32):
             bits = np.zeros((n, self.mask_words * 32), np.uint8)
             bits[:, : self.num_actions] = m
             mt = torch.from_numpy(np.packbits(bits, axis=1, bitorder="little").view(np.int32).copy())
+            if is_t:
+                mask[:, : self.mask_words] = mt
+                mt = mask
         elif mask == "bytes" or is_t:
             mt = torch.from_numpy(m.astype(bool))
             if is_t:
@@ -94,8 +101,15 @@ class OracleEngine:
             if isinstance(obs, torch.Tensor):
                 obs.copy_(ot.view_as(obs))
                 ot = obs
-        return StepOut(out_states, mt, torch.from_numpy(m.sum(1).astype(np.int32)), torch.from_numpy(term),
-                       torch.from_numpy(flags), torch.from_numpy(scores), nxt, None, ot)
+        res = {"legal_count": torch.from_numpy(m.sum(1).astype(np.int32)), "terminal": torch.from_numpy(term),
+               "flags": torch.from_numpy(flags), "scores": torch.from_numpy(scores), "next_action": nxt}
+        for name, val in res.items():                  # like the engine: caller-owned buffers are written in place
+            dst = getattr(buffers, name, None) if buffers is not None else None
+            if dst is not None and val is not None:
+                dst[:n].copy_(val)
+                res[name] = dst
+        return StepOut(out_states, mt, res["legal_count"], res["terminal"], res["flags"], res["scores"], res["next_action"],
+                       None, ot)
 
     def legal_mask(self, states, fmt="bytes", **kw):
         return self.step(states, None, mask=fmt, **kw)

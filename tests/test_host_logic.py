@@ -105,8 +105,17 @@ def test_vector_env_gym_contract():
         if not terminated.any():
             assert "final_info" not in info
     assert finished >= 6
+    # an illegal action for ONE env raises and leaves every env where it was (legal envs do not advance half-way)
+    poss = env.get_attr("ai_possible_indexes")
+    acts = np.array([p[0] for p in poss])
+    acts[3] = next(a for a in range(2522) if a not in set(poss[3]))
+    before = env.states.clone()
     with pytest.raises(ValueError):
-        env.step(np.full(6, 2521))
+        env.step(acts)
+    assert (env.states == before).all() and env.get_attr("ai_possible_indexes") == poss
+    acts[3] = poss[3][-1]
+    env.step(acts)                                          # ... and the env is still usable
+    assert not (env.states == before).all()
     env.close()
 
 
