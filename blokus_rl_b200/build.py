@@ -24,6 +24,16 @@ SMALL_SIZES = [5, 6, 7]          # thread-per-env kernels on 64-bit bitboards (c
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
+def kernel_source_hash() -> str:
+    """sha256 over the CUDA sources and the ABI header: identifies the kernels a profile / traffic figure was taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(DEPS, key=lambda p: p.name):
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    return h.hexdigest()[:16]
+
+
 def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None) -> Path:
     if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
         return OUT

@@ -171,6 +171,36 @@ class GpuPuct:
         self.used += self.B
         self.launches += 3
 
+    def run(self, simulations: int, cpuct: float = 1.0, epsilon_fix: bool = True, chain: int = 1) -> None:
+        """``simulations`` simulations of every tree.  With ``chain = K > 1`` (and a graph-safe evaluator) K consecutive
+        simulations are captured into ONE CUDA graph, so a small forest (the reference's single search,
+        players/mcts_player.py:15-22, is B = 1) pays one graph launch per K simulations instead of 3 K kernel launches."""
+        done = 0
+        chain = max(1, min(int(chain), simulations))
+        if chain > 1 and self.use_cuda_graph:
+            while self._eager_runs < 2 and done < simulations:
+                self.simulate(cpuct, epsilon_fix)
+                done += 1
+            key = (float(cpuct), bool(epsilon_fix), chain)
+            while simulations - done >= chain:
+                if self.used + chain * self.B > self.node_cap:
+                    raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
+                g = self._graphs.get(key)
+                if g is None:
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize(self.eng.device)
+                    with torch.cuda.graph(g):
+                        for _ in range(chain):
+                            self._simulate_eager(cpuct, epsilon_fix)
+                    self._graphs[key] = g
+                g.replay()
+                self.used += chain * self.B
+                self.launches += 3 * chain
+                done += chain
+        while done < simulations:
+            self.simulate(cpuct, epsilon_fix)
+            done += 1
+
     def advance(self, actions: torch.Tensor) -> None:
         """Make the child under ``actions[t]`` the root of tree t (``-1`` leaves a tree where it is)."""
         acts = actions.to(torch.int32).contiguous()

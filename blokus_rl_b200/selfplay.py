@@ -75,7 +75,8 @@ def self_play_gpu(engine, evaluator=None, num_games: int = 256, num_mcts_sims: i
     """Same contract as :func:`self_play_batched`, with the search trees resident on the GPU
     (:class:`blokus_rl_b200.gpu_puct.GpuPuct`): the host only samples one move per game per ply."""
     from .gpu_puct import GpuPuct
-    rng = rng or np.random.default_rng()
+    # `rng` may be one generator per game (sharded runs: game g always draws from its own stream, whatever the partition)
+    rngs = list(rng) if isinstance(rng, (list, tuple)) else [rng or np.random.default_rng()] * num_games
     A, P = engine.num_actions, engine.num_players
     search = GpuPuct(engine, evaluator or UniformEvaluator(), num_trees=num_games,
                      max_simulations=(num_mcts_sims + 1) * max_plies + 2, mean_edges_per_node=mean_edges_per_node)
@@ -85,8 +86,7 @@ def self_play_gpu(engine, evaluator=None, num_games: int = 256, num_mcts_sims: i
     first = True
     plies = 0
     while not done.all() and plies < max_plies:
-        for _ in range(num_mcts_sims):
-            search.simulate(cpuct)
+        search.run(num_mcts_sims, cpuct, chain=num_mcts_sims if num_games <= 64 else 1)
         roots = search.root_states()
         obs = engine.observe(roots).cpu().numpy()
         stats = search.root_stats()
@@ -101,13 +101,13 @@ def self_play_gpu(engine, evaluator=None, num_games: int = 256, num_mcts_sims: i
                 dist = np.power(n, 1.0 / temperature)
             dist = dist / dist.sum() if dist.sum() > 0 else np.full(len(ids), 1.0 / len(ids))
             if first:
-                dist = dist * (1 - dirichlet_weight) + rng.dirichlet(dirichlet_alpha * np.ones(len(ids), np.float32)) * dirichlet_weight
+                dist = dist * (1 - dirichlet_weight) + rngs[t].dirichlet(dirichlet_alpha * np.ones(len(ids), np.float32)) * dirichlet_weight
             prob = dist.astype(np.float32)
             mask = np.zeros(A, dtype=np.float64)
             mask[ids] = 1
             data[t].append([obs[t], mask, prob, None])
             p64 = prob.astype(np.float64)
-            acts[t] = int(ids[rng.choice(len(ids), p=p64 / p64.sum())])
+            acts[t] = int(ids[rngs[t].choice(len(ids), p=p64 / p64.sum())])
         first = False
         search.advance(torch.as_tensor(acts, device=engine.device))
         flags, term, _ = engine.game_ended(search.root_states())

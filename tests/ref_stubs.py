@@ -4,7 +4,14 @@ import sys
 import types
 from pathlib import Path
 
-REFERENCE = Path("/root/reference")
+# The reference's own Python package: the source tree in the build container, or its `pip install --no-deps --target
+# baseline/_ref` copy (git-ignored, but it travels to the GPU box with the snapshot), whichever exists.
+_ROOT = Path(__file__).resolve().parents[1]
+import os
+_CANDIDATES = ([Path(os.environ["BLOKUS_REF_DIR"])] if os.environ.get("BLOKUS_REF_DIR") else []) + \
+    [Path("/root/reference"), _ROOT / "baseline" / "_ref"]
+REFERENCE = next((p for p in _CANDIDATES
+                  if (p / "blokus_rl" / "alphazero" / "mcts.py").exists()), Path("/root/reference"))
 
 
 def available() -> bool:

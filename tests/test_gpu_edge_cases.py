@@ -100,3 +100,60 @@ def test_mask_only_on_finished_states(engine20, oracle20):
     out = eng.step(words, torch.zeros(1, dtype=torch.int32, device="cuda"), mask="bytes", auto_reset=True)
     assert int(out.flags[0]) == 3                # stepping a finished game: illegal + done, state unchanged
     assert (words.cpu().numpy().view(np.uint32)[0] == orc.pack(o)).all()
+
+
+def test_graph_replay_overlapping_eager_launches_on_another_stream(engine20):
+    """A captured step replayed on stream A while eager steps (and playouts) of the SAME engine run on stream B: every
+    launch draws its envs from its own work-queue slot (one per stream, one per graph capture), so nothing is skipped or
+    stepped twice.  250 + 250 overlapping launches must leave exactly the states a serial run leaves."""
+    eng, n, K, seed = engine20, 16384, 250, 77
+    dev = eng.device
+
+    def fresh(sd):
+        st = eng.new_states(n)
+        buf = eng.make_buffers(n, "bits", sample=True)
+        eng.step(st, None, buffers=buf, mask="bits", sample=True, seed=sd)
+        return st, buf
+
+    def one(st, buf, sd):
+        return eng.step(st, buf.next_action, buffers=buf, mask="bits", sample=True, seed=sd, auto_reset=True)
+
+    # serial reference on the default stream
+    (ra, ba), (rb, bb) = fresh(seed), fresh(seed + 1)
+    for _ in range(K):
+        one(ra, ba, seed)
+        one(rb, bb, seed + 1)
+    torch.cuda.synchronize()
+    # the same two runs, overlapping
+    (sa, fa), (sb, fb) = fresh(seed), fresh(seed + 1)
+    torch.cuda.synchronize()
+    st_a, st_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st_a):
+        one(sa, fa, seed)                               # capture only records
+    roots = eng.new_states(64)
+    for k in range(K):
+        with torch.cuda.stream(st_a):
+            g.replay()
+        with torch.cuda.stream(st_b):
+            one(sb, fb, seed + 1)
+            if k % 50 == 0:
+                eng.rollout(roots, 8, seed=k)           # the playout kernel shares the engine's queue slots too
+    torch.cuda.synchronize()
+    assert torch.equal(sa, ra) and torch.equal(sb, rb)
+    assert torch.equal(fa.next_action, ba.next_action) and torch.equal(fb.mask_raw, bb.mask_raw)
+
+
+def test_reused_buffers_are_validated(engine20):
+    eng = engine20
+    small = eng.make_buffers(8, "bytes", sample=True)
+    s = eng.new_states(16)
+    with pytest.raises(ValueError):
+        eng.step(s, None, buffers=small, mask=None)                     # per-env outputs made for 8 envs, 16 stepped
+    roots = eng.new_states(4)
+    with pytest.raises(ValueError):
+        eng.rollout(roots, 2, out_states=roots)                         # aliasing is only defined for per_root == 1
+    eng.rollout(roots, 1, stop_player=1, out_states=roots)
+    cur = torch.cuda.current_device()
+    eng.step(s, None, mask="bits")
+    assert torch.cuda.current_device() == cur                           # entry points leave the caller's device alone

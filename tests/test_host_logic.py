@@ -136,8 +136,12 @@ from oracle_engine import OracleEngine
 from blokus_rl_b200 import distributed as D
 D.init("gloo")
 shard = D.shard_from_env(10)
-local = D.random_play_shard(OracleEngine(7, 2), shard, plies=12, seed=99)
+eng = OracleEngine(7, 2)
+local = D.random_play_shard(eng, shard, plies=12, seed=99)
 total = D.reduce_counters(local)
+# playouts shard by ROOT index (global playout ids in the RNG key): 6 mid-game roots x 5 playouts
+rc, _ = D.rollout_shard(eng, D.shard_from_env(6), 5, seed=7, root_plies=2)
+total["rollouts"] = D.reduce_counters(rc, D.ROLLOUT_COUNTERS)
 if shard.rank == 0:
     print("RESULT " + json.dumps(total))
 '''
@@ -159,6 +163,8 @@ def test_two_rank_gloo_run_equals_single_rank_run():
     (global env ids make the trajectories partition-invariant)."""
     one, two = _run_world(1), _run_world(2)
     assert one == two and one["steps"] == 120 and one["games"] > 0 and one["illegal"] == 0
+    r = one["rollouts"]
+    assert r["playouts"] == 30 and r["plies"] > 30 and r["wins_p0"] + r["wins_p1"] >= 30
 
 
 def test_vector_env_four_players_agent_not_first():
