@@ -159,7 +159,7 @@ def summarise(tag: str):
     from blokus_rl_b200.build import kernel_source_hash
     rep = OUT / f"{tag}_all.ncu-rep"
     meta = json.loads((OUT / f"{tag}_profile_meta.json").read_text())
-    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     launches = rows[2:]
@@ -202,10 +202,12 @@ def summarise(tag: str):
                     i = hdr.index(w)
                     lines.append(f"  {w:80s} {r[i]:>16s} {units[i]}")
             dur = val('gpu__time_duration.sum')
-            dur_us = None if dur is None else (dur / 1e3 if units[hdr.index('gpu__time_duration.sum')] in ("ns", "nsecond") else dur)
+            tunit = units[hdr.index('gpu__time_duration.sum')]
+            dur_us = None if dur is None else dur * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3,
+                                                     "s": 1e6, "second": 1e6}[tunit]
             tb = (val('dram__bytes_read.sum') or 0) + (val('dram__bytes_write.sum') or 0)
             bunit = units[hdr.index('dram__bytes_read.sum')] if 'dram__bytes_read.sum' in hdr else "byte"
-            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(bunit, 1)
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[bunit]
             inst = val('smsp__inst_executed.sum')
             rec = {"kernel": r[kn][:80], "traffic": int(tb * scale), "duration_us": dur_us,
                    "issue_slot_pct": val('smsp__issue_active.avg.pct_of_peak_sustained_active'),
