@@ -38,8 +38,11 @@ extern "C" {
 /* ABI history: 1 = first release of this round; 2 = blk_step_args grew `obs` (fused observation output) and `state_index`
  * (step states out of a pool), blk_rollout_args grew `options`, BLK_OPT_WARP_KERNELS, blk_puct_forest grew `node_uniform`
  * and a 6th counter, blk_puct_expand_args grew `fuse_backup`.  All additions are trailing fields: zero-initialised structs keep
- * their version-1 meaning. */
-#define BLK_ABI_VERSION 2
+ * their version-1 meaning.
+ * 3 = blk_puct_forest grew the board-keyed node table (hash_table, hash_capacity, node_hash, node_tree) and edge_vl;
+ * blk_puct_search / blk_puct_reroot (whole simulations inside one kernel); work-queue slots are per stream / per graph capture;
+ * every entry point restores the caller's current device. */
+#define BLK_ABI_VERSION 3
 
 typedef enum {
     BLK_OK = 0,
@@ -198,6 +201,14 @@ typedef struct {
     int32_t *path_node;           /* [B][max_depth] node of each path edge */
     int8_t *node_uniform;         /* [nodes] 1 = expanded with the uniform prior: P = 1/nedge for every edge, edge_p is not
                                      written (saves a quarter of the expansion's stores and a third of the selection's loads) */
+    /* Board-keyed node table (blk_puct_search / blk_puct_reroot; NULL for the lockstep kernels, which key nodes by path):
+     * the reference files a node under hash(board cells) only (mcts.py:37, blokus_wrapper.py:217-218), so two move orders
+     * that reach the same board share one node.  Open addressing; an entry is node + 1, 0 = empty. */
+    int32_t *hash_table;          /* [hash_capacity], zeroed by the caller */
+    int32_t hash_capacity;        /* power of two, >= 2 * node_capacity */
+    uint64_t *node_hash;          /* [nodes] 64-bit hash of (tree, board rows) */
+    int32_t *node_tree;           /* [nodes] tree the node belongs to (equal boards of different trees stay apart) */
+    int32_t *edge_vl;             /* [edges] virtual-loss counters, zeroed by the caller (leaf-parallel search only) */
 } blk_puct_forest;
 
 typedef struct {
@@ -220,6 +231,23 @@ typedef struct {
                                      counters[] then needs 6 entries ([5] = pool slots of the last simulation still to be counted) */
 } blk_puct_expand_args;
 
+/* Whole simulations inside ONE kernel (no launch per tree level, no host in the loop): for the evaluators that need no
+ * network -- the uniform prior with zero value of the reference's "mcts" arena player (models/dumbnet.py:14-21,
+ * compare_arena.py:87-95), optionally with the mean of `playouts_per_leaf` uniform-random playouts as the value. */
+typedef struct {
+    int32_t num_sims;             /* simulations per tree in this launch */
+    double cpuct;                 /* root-level exploration constant (deeper levels use 1: mcts.py:50-52) */
+    int32_t epsilon_fix;
+    uint32_t *pool;               /* [node_capacity][state_words] state pool (node_state indexes it) */
+    int32_t warps_per_tree;       /* 1: simulations of a tree run one after the other, exactly as the reference's (visit
+                                     counts, Q and per-simulation scores are reproduced).  > 1 (<= 16): that many warps
+                                     search the same tree at once with virtual loss -- leaf-parallel, NOT the reference's
+                                     visit order; needs edge_vl */
+    int32_t playouts_per_leaf;    /* 0: leaf value = 0 (DumbNet); k > 0: mean 3/1/-1 vector of k uniform-random playouts */
+    uint64_t seed;                /* playout RNG key (stream 2) */
+    double virtual_loss;          /* value a pending visit is counted as for its edge (leaf-parallel); 0 -> 1.0 */
+} blk_puct_search_args;
+
 const char *blk_puct_last_error(void);
 /* MCTS.simulate, selection half: mcts.py:39-52 for every tree, down to a leaf / unopened edge / terminal node. */
 int blk_puct_select(const blk_puct_forest *f, double cpuct, int32_t epsilon_fix, void *stream);
@@ -231,6 +259,14 @@ int blk_puct_backup(const blk_puct_forest *f, void *stream);
 int blk_puct_best(const blk_puct_forest *f, int32_t *best_action, double *best_visits, void *stream);
 /* After a real move: the child under `actions[t]` becomes the root (tree reuse, players/mcts_player.py:15-22). */
 int blk_puct_advance(const blk_puct_forest *f, const int32_t *actions, void *stream);
+
+/* MCTS.simulate x num_sims for every tree, selection, env transition, legal-move expansion and backup fused in one
+ * kernel (one warp, or `warps_per_tree` warps, per tree); nodes are keyed by board cells like the reference's dict
+ * (mcts.py:37), a simulation that reaches a known board continues its descent there.  Needs the engine (env tables). */
+int blk_puct_search(blk_engine *h, const blk_puct_forest *f, const blk_puct_search_args *args, void *stream);
+/* Tree reuse the way the reference gets it (its dict outlives the move: players/mcts_player.py:15-25): the root of tree t
+ * becomes the node filed under the board of states[t] if the tree has one, else a fresh unexpanded node. */
+int blk_puct_reroot(blk_engine *h, const blk_puct_forest *f, const blk_puct_search_args *args, const uint32_t *states, void *stream);
 
 #ifdef __cplusplus
 }
