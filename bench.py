@@ -563,7 +563,7 @@ def run_search_workload(args, D: Dist, eng):
         sims = args.sims
         roots = BD.midgame_roots(eng, shard.lo, shard.n)
         search = GpuPuct(eng, num_trees=shard.n, max_simulations=(args.steps + max(args.warmup, 3)) * sims + 8,
-                         mean_edges_per_node=420)
+                         mean_edges_per_node=420, fused=not args.lockstep, warps_per_tree=1 if args.lockstep else args.warps_per_tree)
         search.set_roots(roots)
         for _ in range(max(args.warmup, 3)):
             search.run(sims, chain=args.chain)
@@ -582,7 +582,8 @@ def run_search_workload(args, D: Dist, eng):
         h_best = torch.empty(nroots, dtype=torch.int32).pin_memory()
         d_roots = torch.empty_like(roots)
         esteps = max(3, min(args.steps, 10))
-        s2 = GpuPuct(eng, num_trees=shard.n, max_simulations=sims + 8, mean_edges_per_node=420)
+        s2 = GpuPuct(eng, num_trees=shard.n, max_simulations=sims + 8, mean_edges_per_node=420, fused=not args.lockstep,
+                     warps_per_tree=1 if args.lockstep else args.warps_per_tree)
         s2.set_roots(roots); s2.run(sims, chain=args.chain)         # graphs captured outside the timed region
         D.sync_all()
         e0.record()
@@ -601,9 +602,11 @@ def run_search_workload(args, D: Dist, eng):
         mean_plies = None
         e2e = {"value": world * units * esteps / (ems * 1e-3), "unit": "simulations/s", "h2d_bytes_per_step": roots.numel() * 4 * world,
                "d2h_bytes_per_step": 4 * nroots * world, "steps": esteps}
-        launches = 3 * sims * args.steps
-        workload = (f"{nroots} PUCT searches per GPU in lockstep from 24-ply roots (global root ids), {sims} simulations per step, "
-                    f"uniform prior (DumbNet, config/mcts_blokus.yml), trees on the GPU (blk_puct_*), {args.chain} simulations per CUDA graph")
+        launches = (3 * sims if args.lockstep else 2) * args.steps
+        how = (f"lockstep kernels (blk_puct_select / blk_step / blk_puct_expand), {args.chain} simulations per CUDA graph" if args.lockstep
+               else f"whole simulations inside one kernel (blk_puct_search), {args.warps_per_tree} warp(s) per tree, nodes keyed by board")
+        workload = (f"{nroots} PUCT searches per GPU from 24-ply roots (global root ids), {sims} simulations per step, "
+                    f"uniform prior (DumbNet, config/mcts_blokus.yml), trees on the GPU: {how}")
         prof, prof_note = None, "no single dominant kernel (select / blk_step / expand)"
     clocks = sampler.stop() if sampler else None
     totals = BD.reduce_counters(local_c, names)
@@ -758,23 +761,43 @@ def extra_workloads(eng, torch):
             agent_step()
         extra[f"ppo_numpy_surface_agent_steps_per_s_{E}_envs"] = E * reps / (time.perf_counter() - t0)
     e7.close()
-    # device-resident PUCT forest (config/mcts_blokus.yml player: MCTS with the uniform DumbNet prior), B trees in lockstep
+    # device-resident PUCT forest (config/mcts_blokus.yml player: MCTS with the uniform DumbNet prior)
     from blokus_rl_b200.gpu_puct import GpuPuct
-    for B, sims, chain in ((4096, 50, 1), (1, 200, 50), (4, 200, 50), (16, 200, 50)):
+
+    def roots_after(B, plies=24, seed=5):
         roots = eng.new_states(B)
-        o = eng.step(roots, None, mask=None, sample=True, seed=5)
-        for _ in range(24):
-            o = eng.step(roots, o.next_action, mask=None, sample=True, seed=5)
-        search = GpuPuct(eng, num_trees=B, max_simulations=5 * sims + 8, mean_edges_per_node=420)
-        search.set_roots(roots)
-        sec = timed(lambda: search.run(sims, chain=chain), 1)
+        o = eng.step(roots, None, mask=None, sample=True, seed=seed)
+        for _ in range(plies):
+            o = eng.step(roots, o.next_action, mask=None, sample=True, seed=seed)
+        return roots
+    # (name, trees, simulations per move, fused kernel?, warps per tree, simulations per CUDA graph on the lockstep path)
+    for name, B, sims, fused, wpt, chain in (("mcts_simulations_per_s", 4096, 50, False, 1, 1),
+                                             ("mcts_simulations_per_s_fused_B4096", 4096, 50, True, 1, 1),
+                                             ("mcts_simulations_per_s_lockstep_graph_B1", 1, 200, False, 1, 50),
+                                             ("mcts_simulations_per_s_B1", 1, 200, True, 1, 1),
+                                             ("mcts_simulations_per_s_B4", 4, 200, True, 1, 1),
+                                             ("mcts_simulations_per_s_B16", 16, 200, True, 1, 1),
+                                             ("mcts_simulations_per_s_B1_leaf_parallel_8_warps", 1, 200, True, 8, 1),
+                                             ("mcts_simulations_per_s_B1_leaf_parallel_16_warps", 1, 200, True, 16, 1)):
+        roots = roots_after(B)
+        search = GpuPuct(eng, num_trees=B, max_simulations=5 * sims + 8, mean_edges_per_node=420, fused=fused, warps_per_tree=wpt)
+
+        def move():                                    # one move's search: fresh tree, `sims` simulations, the chosen action
+            search.set_roots(roots)
+            search.run(sims, chain=chain)
+            return search.best_actions_device()
+        sec = timed(move, 3)
         search.check()
-        extra["mcts_simulations_per_s" if B == 4096 else f"mcts_simulations_per_s_B{B}"] = B * sims / sec
+        extra[name] = B * sims / sec
         del search
-    extra["mcts_workload"] = ("B PUCT searches in lockstep from 24-ply roots, uniform prior (DumbNet), trees on the GPU (blk_puct_*); "
-                              "B = 4096: 50 simulations eager; B = 1, 4, 16: 200 simulations per move (players/mcts_player.py, "
-                              "compare_arena.py:87-95), 50 simulations per CUDA graph.  CPU context: the reference's mcts.py over the "
-                              "C oracle does ~2.9e3 simulations/s on one core (tools/ref_mcts_cpu_rate.py)")
+    extra["mcts_workload"] = ("B PUCT searches from 24-ply roots, uniform prior (DumbNet), trees on the GPU.  mcts_simulations_per_s: "
+                              "4096 trees in lockstep, 3 launches per simulation (blk_puct_select / blk_step / blk_puct_expand) -- the "
+                              "path a torch net uses; *_fused_*, *_B1/B4/B16: whole simulations inside one kernel (blk_puct_search), a "
+                              "warp per tree, 200 simulations per move as in players/mcts_player.py + compare_arena.py:87-95, "
+                              "reference visit order; *_leaf_parallel_*: the same single tree searched by 8 / 16 warps at once with "
+                              "virtual loss (not the reference's visit order).  Each figure includes set_roots and the final argmax.  "
+                              "CPU context: the reference's mcts.py over the C oracle does ~2.9e3 simulations/s on one core "
+                              "(tools/ref_mcts_cpu_rate.py)")
     return extra
 
 
@@ -793,7 +816,9 @@ def main():
     ap.add_argument("--roots", type=int, default=1024, help="roots / trees per GPU (workloads rollouts, puct)")
     ap.add_argument("--per-root", type=int, default=1024, help="playouts per root (workload rollouts)")
     ap.add_argument("--sims", type=int, default=25, help="simulations per tree and step (workload puct)")
-    ap.add_argument("--chain", type=int, default=1, help="simulations captured per CUDA graph (workload puct)")
+    ap.add_argument("--chain", type=int, default=1, help="simulations captured per CUDA graph (workload puct --lockstep)")
+    ap.add_argument("--lockstep", action="store_true", help="workload puct: the 3-launch lockstep kernels instead of the fused search")
+    ap.add_argument("--warps-per-tree", type=int, default=1, help="workload puct: > 1 = leaf-parallel fused search with virtual loss")
     ap.add_argument("--e2e-halves", type=int, default=2, help="part-batches pipelined on separate streams in the e2e leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the rollout / leaf-expansion extras")

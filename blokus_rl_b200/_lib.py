@@ -17,12 +17,13 @@ BLK_MASK_NONE, BLK_MASK_BITS, BLK_MASK_BYTES, BLK_MASK_INDICES = 0, 1, 2, 3
 BLK_OPT_AUTO_RESET = 1
 BLK_OPT_WARP_KERNELS = 2
 BLK_FLAG_DONE, BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED = 1, 2, 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "blk_last_error", "blk_abi_version", "blk_create", "blk_destroy", "blk_get_info", "blk_action_to_cells",
     "blk_reset", "blk_step", "blk_observe", "blk_board_contents", "blk_game_ended", "blk_rollout",
     "blk_puct_last_error", "blk_puct_select", "blk_puct_expand", "blk_puct_backup", "blk_puct_best", "blk_puct_advance",
+    "blk_puct_search", "blk_puct_reroot",
 )
 
 
@@ -62,7 +63,16 @@ class BlkPuctForest(C.Structure):
                 [(n, C.c_void_p) for n in ("node_edge0", "node_nedge", "node_state", "node_mover", "node_terminal",
                                            "node_term_value", "edge_action", "edge_child", "edge_n", "edge_q", "edge_p",
                                            "root", "path", "path_len", "status", "leaf_node", "leaf_edge", "src_slot",
-                                           "step_action", "scores", "counters", "node_sum_n", "path_node", "node_uniform")])
+                                           "step_action", "scores", "counters", "node_sum_n", "path_node", "node_uniform",
+                                           "hash_table")] +
+                [("hash_capacity", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("node_hash", "node_tree", "edge_vl", "node_front")])
+
+
+class BlkPuctSearchArgs(C.Structure):
+    _fields_ = [("num_sims", C.c_int32), ("cpuct", C.c_double), ("epsilon_fix", C.c_int32), ("pool", C.c_void_p),
+                ("warps_per_tree", C.c_int32), ("playouts_per_leaf", C.c_int32), ("seed", C.c_uint64),
+                ("virtual_loss", C.c_double)]
 
 
 class BlkPuctExpandArgs(C.Structure):
@@ -108,6 +118,8 @@ def load() -> C.CDLL:
     lib.blk_puct_backup.argtypes = [C.POINTER(BlkPuctForest), C.c_void_p]
     lib.blk_puct_best.argtypes = [C.POINTER(BlkPuctForest), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.blk_puct_advance.argtypes = [C.POINTER(BlkPuctForest), C.c_void_p, C.c_void_p]
+    lib.blk_puct_search.argtypes = [C.c_void_p, C.POINTER(BlkPuctForest), C.POINTER(BlkPuctSearchArgs), C.c_void_p]
+    lib.blk_puct_reroot.argtypes = [C.c_void_p, C.POINTER(BlkPuctForest), C.POINTER(BlkPuctSearchArgs), C.c_void_p, C.c_void_p]
     if lib.blk_abi_version() != ABI_VERSION:
         raise EngineError("libblokus_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -16,7 +16,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "build"
 OUT = PKG / "libblokus_b200.so"
-DEPS = [CSRC / "blk_engine.cu", CSRC / "blk_inst.cu", CSRC / "blk_puct.cu", CSRC / "blk_kernels.cuh", CSRC / "blk_orient.inc",
+DEPS = [CSRC / "blk_engine.cu", CSRC / "blk_inst.cu", CSRC / "blk_puct.cu", CSRC / "blk_kernels.cuh", CSRC / "blk_search.cuh", CSRC / "blk_orient.inc",
         CSRC / "blk_small.cu", CSRC / "blk_small_fields.inc",
         ROOT / "include" / "blokus_b200.h"]
 GEOMETRIES = [(20, 4), (20, 2), (14, 4), (14, 2), (7, 2), (0, 0)]

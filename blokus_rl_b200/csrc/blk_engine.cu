@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "blk_kernels.cuh"
+#include "blk_search.cuh"
 
 using namespace blk;
 
@@ -243,6 +244,8 @@ struct blk_engine {
     int step_blocks_per_sm = 0, rollout_blocks_per_sm = 0;
     bool special = false;
     KernelSet ks = {};                               // step[mask format variant][sampler], rollout
+    SearchKernelSet sk = {};                         // fused PUCT search / reroot (blk_search.cuh)
+    int search_smem_per_warp = 0;
     bool small = false;                              // N <= 7: thread-per-env kernels (blk_small.cu) for the common formats
     SmallKernelSet sks = {};
     unsigned char *d_small = nullptr;                // ocells64[92] | first_mask[mw]
@@ -437,12 +440,13 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     // specialised kernels for the geometries the reference's configs name, runtime-dimension kernels otherwise
     const int N = cfg->board_size, P = cfg->num_players;
     int geom = 0;
-    if (N == 20 && P == 4) { h->ks = kernels_20_4(); geom = 1; }
-    else if (N == 20 && P == 2) { h->ks = kernels_20_2(); geom = 2; }
-    else if (N == 14 && P == 4) { h->ks = kernels_14_4(); geom = 3; }
-    else if (N == 14 && P == 2) { h->ks = kernels_14_2(); geom = 4; }
-    else if (N == 7 && P == 2) { h->ks = kernels_7_2(); geom = 5; }
-    else h->ks = kernels_0_0();
+    if (N == 20 && P == 4) { h->ks = kernels_20_4(); h->sk = search_kernels_20_4(); geom = 1; }
+    else if (N == 20 && P == 2) { h->ks = kernels_20_2(); h->sk = search_kernels_20_2(); geom = 2; }
+    else if (N == 14 && P == 4) { h->ks = kernels_14_4(); h->sk = search_kernels_14_4(); geom = 3; }
+    else if (N == 14 && P == 2) { h->ks = kernels_14_2(); h->sk = search_kernels_14_2(); geom = 4; }
+    else if (N == 7 && P == 2) { h->ks = kernels_7_2(); h->sk = search_kernels_7_2(); geom = 5; }
+    else { h->ks = kernels_0_0(); h->sk = search_kernels_0_0(); }
+    h->search_smem_per_warp = h->g.warp_smem + 2 * kSearchMaxIds + 8 * kSearchMaxDepth + 64;
     h->special = geom != 0;
     // the attribute is per function, not per engine: only ever raise it (engines of several board sizes coexist)
     static int s_max_smem[16][6] = {};
@@ -452,6 +456,9 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
         for (int f = 0; f < 5 && err == cudaSuccess; ++f)
             for (int sm = 0; sm < 2 && err == cudaSuccess; ++sm)
                 err = cudaFuncSetAttribute(h->ks.step[f][sm], cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem);
+        for (int k = 0; k < 2 && err == cudaSuccess; ++k)
+            err = cudaFuncSetAttribute(h->sk.search[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       h->t.bytes + 16 + (k ? 16 : kSearchTrees) * h->search_smem_per_warp);
         if (err != cudaSuccess) { blk_destroy(h); return fail(BLK_ERR_CUDA, "cudaFuncSetAttribute(smem) failed"); }
         cur_max = h->step_smem;
     }
@@ -670,6 +677,57 @@ int blk_rollout(blk_engine *h, const blk_rollout_args *args, void *stream) {
     }
     const int grid = grid_for(args->n_roots * args->per_root, kRollWarps, h->sm_count, h->rollout_blocks_per_sm);
     h->ks.rollout<<<grid, kRollWarps * 32, h->roll_smem, static_cast<cudaStream_t>(stream)>>>(rp);
+    CUDA_TRY(cudaGetLastError());
+    return BLK_OK;
+}
+
+// ---- fused PUCT search (blk_search.cuh) ----
+namespace {
+int check_search_args(const blk_engine *h, const blk_puct_forest *f, const blk_puct_search_args *a) {
+    if (!h || !f || !a) return fail(BLK_ERR_ARG, "null argument");
+    if (f->num_players != h->g.P || f->num_actions != h->g.A) return fail(BLK_ERR_ARG, "forest geometry differs from the engine's");
+    if (!a->pool) return fail(BLK_ERR_ARG, "the state pool is required");
+    if (!f->hash_table || !f->node_hash || !f->node_tree || !f->node_front || f->hash_capacity < 2 || (f->hash_capacity & (f->hash_capacity - 1)))
+        return fail(BLK_ERR_ARG, "the board-keyed node table (hash_table, node_hash, node_tree, node_front, power-of-two hash_capacity) is required");
+    if (f->hash_capacity < f->node_capacity) return fail(BLK_ERR_ARG, "hash_capacity must be >= node_capacity");
+    return BLK_OK;
+}
+}  // namespace
+
+int blk_puct_search(blk_engine *h, const blk_puct_forest *f, const blk_puct_search_args *a, void *stream) {
+    int rc = check_search_args(h, f, a);
+    if (rc != BLK_OK) return rc;
+    if (f->num_trees <= 0 || a->num_sims <= 0) return BLK_OK;
+    const int wpt = a->warps_per_tree <= 1 ? 1 : a->warps_per_tree;
+    if (wpt > 16) return fail(BLK_ERR_ARG, "warps_per_tree must be <= 16");
+    if (wpt > 1 && !f->edge_vl) return fail(BLK_ERR_ARG, "leaf-parallel search needs edge_vl");
+    if (a->playouts_per_leaf < 0) return fail(BLK_ERR_ARG, "playouts_per_leaf must be >= 0");
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(guard.err);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SearchParams sp;
+    sp.f = *f; sp.a = *a; sp.tables = h->d_tables; sp.t = h->t; sp.g = h->g; sp.reroot_states = nullptr;
+    if (wpt == 1) {
+        const int grid = (f->num_trees + kSearchTrees - 1) / kSearchTrees;
+        h->sk.search[0]<<<grid, kSearchTrees * 32, h->t.bytes + 16 + kSearchTrees * h->search_smem_per_warp, st>>>(sp);
+    } else {
+        h->sk.search[1]<<<f->num_trees, wpt * 32, h->t.bytes + 16 + wpt * h->search_smem_per_warp, st>>>(sp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return BLK_OK;
+}
+
+int blk_puct_reroot(blk_engine *h, const blk_puct_forest *f, const blk_puct_search_args *a, const uint32_t *states, void *stream) {
+    int rc = check_search_args(h, f, a);
+    if (rc != BLK_OK) return rc;
+    if (!states) return fail(BLK_ERR_ARG, "states are required");
+    if (f->num_trees <= 0) return BLK_OK;
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(guard.err);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SearchParams sp;
+    sp.f = *f; sp.a = *a; sp.tables = h->d_tables; sp.t = h->t; sp.g = h->g; sp.reroot_states = states;
+    h->sk.reroot<<<(f->num_trees + kSearchTrees - 1) / kSearchTrees, kSearchTrees * 32, 0, st>>>(sp);
     CUDA_TRY(cudaGetLastError());
     return BLK_OK;
 }

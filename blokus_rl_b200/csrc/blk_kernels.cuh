@@ -802,6 +802,101 @@ struct RParams {
     unsigned long long *queue;
 };
 
+// One uniform-random playout by one warp: from the state in `e` until the game is over (or until it is `stop_player`'s
+// turn).  Sampler: Philox block (ply >> 2, game, stream, 0) under key (key0, key1), word ply & 3, k = mulhi(u, n_legal),
+// k-th legal action in ascending id order.  Returns the plies played; `over` says whether the game ended.
+template <int kN, int kP>
+__device__ __forceinline__ int playout_game(EnvRegs &e, const SmemTables &tb, const Geometry &gg, const Dims &g, uint32_t *fld,
+                                            int lane, uint32_t key0, uint32_t key1, uint32_t stream, int stop_player,
+                                            uint16_t *log, int log_cap, bool &over) {
+    const int N = g.N, P = g.P;
+    const int nf = kN == 20 ? 1665 : gg.nf;
+    const int per = (nf + 31) >> 5;   // contiguous fields per lane for the k-th-bit search (53 at N = 20)
+    int nply = 0;
+    uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+    int rnd_block = -1;
+    over = (e.meta >> 4) & 1u;
+    // the root's mover is evaluated first; afterwards every player gets a try after each placement (R8)
+    int cand = static_cast<int>(e.meta & 15u);
+    cand = cand == 0 ? P - 1 : cand - 1;
+    int tries = 1;
+    uint32_t stuck = 0u;
+#pragma unroll 1
+    while (!over) {
+        cand = (cand + 1 == P) ? 0 : cand + 1;
+        bool has = false;
+        int mine = 0, incl = 0;
+        if (!((stuck >> cand) & 1u)) {
+            uint32_t fr0, dg0;
+            prep_rows(e, cand, g, lane, fr0, dg0);
+            eval_fields<true, false>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
+            __syncwarp();
+            // count legal actions: lane sums popcounts over its contiguous chunk of fields (field order = id order);
+            // "has a move" falls out of the count, so the fields are not OR-reduced separately
+            if (kN == 20) {                 // 1665 fields = 32 x 52 (+1 for lane 31): 13 conflict-free LDS.128 per lane
+                const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 13 * lane;
+#pragma unroll
+                for (int j = 0; j < 13; ++j) {
+                    const uint4 x = f4[j];
+                    mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+                }
+                if (lane == 31) mine += __popc(fld[1664]);
+            } else {
+                for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
+            }
+            incl = warp_incl_scan(mine, lane);
+            has = __shfl_sync(kAllLanes, incl, 31) > 0;
+            // a player without a move never gets one back (others only take cells away, and it places nothing
+            // itself), so it is not evaluated again for the rest of the playout
+            if (!has) stuck |= 1u << cand;
+        }
+        if (!has) {
+            if (--tries > 0) continue;
+            e.meta |= 1u << 4;
+            over = true;
+            break;
+        }
+        e.meta = (e.meta & ~15u) | static_cast<uint32_t>(cand);
+        if (cand == stop_player) break;              // caller's turn: hand the state back
+        const int cnt = __shfl_sync(kAllLanes, incl, 31);
+        const uint32_t ply = e.meta >> 16;
+        if (static_cast<int>(ply >> 2) != rnd_block) {
+            rnd = philox4(ply >> 2, e.game, stream, 0u, key0, key1);
+            rnd_block = static_cast<int>(ply >> 2);
+        }
+        int k = static_cast<int>(__umulhi(philox_word(rnd, ply), static_cast<uint32_t>(cnt)));
+        const int L = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
+        k -= __shfl_sync(kAllLanes, incl - mine, L);
+        // second level: the chunk of lane L, 32 fields at a time
+        const int chunk = kN == 20 ? 52 : per;
+        const int chunk_len = kN == 20 ? (L == 31 ? 53 : 52) : per;
+        int fsel = -1, kk = 0;
+        for (int half = 0; half * 32 < chunk_len; ++half) {
+            const int j = half * 32 + lane;
+            const int i = L * chunk + j;
+            const int c = (j < chunk_len && i < nf) ? __popc(fld[i]) : 0;
+            const int inc2 = warp_incl_scan(c, lane);
+            const uint32_t b = __ballot_sync(kAllLanes, k < inc2);
+            if (b) {
+                const int J = __ffs(b) - 1;
+                kk = k - __shfl_sync(kAllLanes, inc2 - c, J);
+                fsel = L * chunk + half * 32 + J;
+                break;
+            }
+            k -= __shfl_sync(kAllLanes, inc2, 31);
+        }
+        const int bit = kth_set_bit(fld[fsel], kk);
+        if (log != nullptr && lane == 0 && nply < log_cap - 1) log[nply] = static_cast<uint16_t>(tb.foff[fsel] + bit);
+        uint32_t pm; int piece, ncells;
+        decode_field(fsel, bit, tb, lane, pm, piece, ncells);
+        apply_placement(e, cand, pm, piece, ncells);
+        ++nply;
+        tries = P;
+        __syncwarp();
+    }
+    return nply;
+}
+
 template <int kN, int kP>
 __global__ void __launch_bounds__(kRollWarps * 32, BLK_ROLL_MIN_BLOCKS) rollout_kernel(const RParams rp) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -817,11 +912,9 @@ __global__ void __launch_bounds__(kRollWarps * 32, BLK_ROLL_MIN_BLOCKS) rollout_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * gg.warp_smem);
-    const int N = g.N, P = g.P;
-    const int sw = P * N + P + 4;
-    const int nf = kN == 20 ? 1665 : gg.nf;
+    const int P = g.P;
+    const int sw = P * g.N + P + 4;
     const int64_t total = a.n_roots * a.per_root;
-    const int per = (nf + 31) >> 5;   // contiguous fields per lane for the k-th-bit search (53 at N = 20)
 
     for (int64_t gid = next_ticket(rp.queue, lane); gid < total; gid = next_ticket(rp.queue, lane)) {
         const int64_t root = gid / a.per_root;
@@ -829,89 +922,9 @@ __global__ void __launch_bounds__(kRollWarps * 32, BLK_ROLL_MIN_BLOCKS) rollout_
         env_load(e, a.roots + root * sw, g, lane);
         const uint32_t key0 = static_cast<uint32_t>(a.seed);
         const uint32_t key1 = static_cast<uint32_t>(a.seed >> 32) ^ (a.rollout_id_base + static_cast<uint32_t>(gid));
-        int nply = 0;
-        uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
-        int rnd_block = -1;
-        bool over = (e.meta >> 4) & 1u;
-        // the root's mover is evaluated first; afterwards every player gets a try after each placement (R8)
-        int cand = static_cast<int>(e.meta & 15u);
-        cand = cand == 0 ? P - 1 : cand - 1;
-        int tries = 1;
-        uint32_t stuck = 0u;
-#pragma unroll 1
-        while (!over) {
-            cand = (cand + 1 == P) ? 0 : cand + 1;
-            bool has = false;
-            int mine = 0, incl = 0;
-            if (!((stuck >> cand) & 1u)) {
-                uint32_t fr0, dg0;
-                prep_rows(e, cand, g, lane, fr0, dg0);
-                eval_fields<true, false>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, cand), fld, N, lane);
-                __syncwarp();
-                // count legal actions: lane sums popcounts over its contiguous chunk of fields (field order = id order);
-                // "has a move" falls out of the count, so the fields are not OR-reduced separately
-                if (kN == 20) {                 // 1665 fields = 32 x 52 (+1 for lane 31): 13 conflict-free LDS.128 per lane
-                    const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 13 * lane;
-#pragma unroll
-                    for (int j = 0; j < 13; ++j) {
-                        const uint4 x = f4[j];
-                        mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
-                    }
-                    if (lane == 31) mine += __popc(fld[1664]);
-                } else {
-                    for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
-                }
-                incl = warp_incl_scan(mine, lane);
-                has = __shfl_sync(kAllLanes, incl, 31) > 0;
-                // a player without a move never gets one back (others only take cells away, and it places nothing
-                // itself), so it is not evaluated again for the rest of the playout
-                if (!has) stuck |= 1u << cand;
-            }
-            if (!has) {
-                if (--tries > 0) continue;
-                e.meta |= 1u << 4;
-                over = true;
-                break;
-            }
-            e.meta = (e.meta & ~15u) | static_cast<uint32_t>(cand);
-            if (cand == a.stop_player) break;              // caller's turn: hand the state back
-            const int cnt = __shfl_sync(kAllLanes, incl, 31);
-            const uint32_t ply = e.meta >> 16;
-            if (static_cast<int>(ply >> 2) != rnd_block) {
-                rnd = philox4(ply >> 2, e.game, 1u, 0u, key0, key1);
-                rnd_block = static_cast<int>(ply >> 2);
-            }
-            int k = static_cast<int>(__umulhi(philox_word(rnd, ply), static_cast<uint32_t>(cnt)));
-            const int L = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
-            k -= __shfl_sync(kAllLanes, incl - mine, L);
-            // second level: the chunk of lane L, 32 fields at a time
-            const int chunk = kN == 20 ? 52 : per;
-            const int chunk_len = kN == 20 ? (L == 31 ? 53 : 52) : per;
-            int fsel = -1, kk = 0;
-            for (int half = 0; half * 32 < chunk_len; ++half) {
-                const int j = half * 32 + lane;
-                const int i = L * chunk + j;
-                const int c = (j < chunk_len && i < nf) ? __popc(fld[i]) : 0;
-                const int inc2 = warp_incl_scan(c, lane);
-                const uint32_t b = __ballot_sync(kAllLanes, k < inc2);
-                if (b) {
-                    const int J = __ffs(b) - 1;
-                    kk = k - __shfl_sync(kAllLanes, inc2 - c, J);
-                    fsel = L * chunk + half * 32 + J;
-                    break;
-                }
-                k -= __shfl_sync(kAllLanes, inc2, 31);
-            }
-            const int bit = kth_set_bit(fld[fsel], kk);
-            if (a.action_log != nullptr && lane == 0 && nply < a.log_stride - 1)
-                a.action_log[gid * a.log_stride + nply] = static_cast<uint16_t>(tb.foff[fsel] + bit);
-            uint32_t pm; int piece, ncells;
-            decode_field(fsel, bit, tb, lane, pm, piece, ncells);
-            apply_placement(e, cand, pm, piece, ncells);
-            ++nply;
-            tries = P;
-            __syncwarp();
-        }
+        bool over;
+        const int nply = playout_game<kN, kP>(e, tb, gg, g, fld, lane, key0, key1, 1u, a.stop_player,
+                                              a.action_log != nullptr ? a.action_log + gid * a.log_stride : nullptr, a.log_stride, over);
         int fscore;
         const float tval = terminal_value(e, g, lane, fscore);
         const uint32_t win = __ballot_sync(kAllLanes, lane < P && tval > 0.f);

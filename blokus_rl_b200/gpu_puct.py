@@ -22,12 +22,29 @@ from .mcts import UniformEvaluator
 
 class GpuPuct:
     def __init__(self, engine, evaluator=None, num_trees: int = 256, max_simulations: int = 4096,
-                 mean_edges_per_node: int = 384, max_depth: int = 96, use_cuda_graph: bool = True):
+                 mean_edges_per_node: int = 384, max_depth: int = 96, use_cuda_graph: bool = True,
+                 fused: bool | None = None, warps_per_tree: int = 1, virtual_loss: float = 1.0):
         """``max_simulations`` bounds nodes per tree (one per simulation + roots); ``mean_edges_per_node`` sizes the
         edge arrays (32 B per edge; 20x20 positions have 58-760 legal moves, ~170 on average over a game and
-        300-450 around plies 8-24).  Overflow is detected on the device and reported by :meth:`check`."""
+        300-450 around plies 8-24).  Overflow is detected on the device and reported by :meth:`check`.
+
+        ``fused`` (default: on whenever the evaluator needs no network -- :class:`UniformEvaluator`, the reference's DumbNet,
+        or :class:`RolloutEvaluator`): whole simulations run inside ONE kernel (``blk_puct_search``, csrc/blk_search.cuh), a
+        warp per tree, nodes keyed by board cells like the reference's dict, so ``run(k)`` is one launch whatever k is.
+        ``warps_per_tree > 1`` (fused only) searches each tree with that many warps at once under virtual loss:
+        leaf-parallel, faster for few trees, NOT the reference's visit order."""
         self.eng = engine
         self.evaluator = evaluator or UniformEvaluator()
+        ev = self.evaluator
+        self.playouts_per_leaf = int(getattr(ev, "per_leaf", 0)) if type(ev).__name__ == "RolloutEvaluator" else 0
+        can_fuse = type(ev).__name__ in ("UniformEvaluator", "RolloutEvaluator") and bool(getattr(ev, "uniform_prior", False))
+        if fused and not can_fuse:
+            raise ValueError("fused search needs an evaluator without a network (UniformEvaluator or RolloutEvaluator)")
+        self.fused = can_fuse if fused is None else bool(fused)
+        self.warps_per_tree = int(warps_per_tree) if self.fused else 1
+        if not 1 <= self.warps_per_tree <= 16:
+            raise ValueError("warps_per_tree must be in 1..16")
+        self.virtual_loss = float(virtual_loss)
         self.B, self.P, self.A = num_trees, engine.num_players, engine.num_actions
         self._lib = _lib.load()
         dev = engine.device
@@ -65,6 +82,14 @@ class GpuPuct:
             "node_sum_n": torch.empty(self.node_cap, **f64), "path_node": torch.empty((self.B, max_depth), **i32),
             "node_uniform": torch.zeros(self.node_cap, dtype=torch.int8, device=dev),
         }
+        # board-keyed node table of the fused search (the reference keys its dict by board cells: mcts.py:37)
+        self.hash_cap = 1 << max(4, (2 * self.node_cap - 1).bit_length()) if self.fused else 0
+        if self.fused:
+            t["hash_table"] = torch.zeros(self.hash_cap, **i32)
+            t["node_hash"] = torch.empty(self.node_cap, dtype=torch.int64, device=dev)
+            t["node_tree"] = torch.empty(self.node_cap, **i32)
+            t["edge_vl"] = torch.zeros(self.edge_cap if self.warps_per_tree > 1 else 1, **i32)
+            t["node_front"] = torch.zeros(self.node_cap, **i32)
         self.pool = torch.empty((self.node_cap, engine.state_words), dtype=torch.int32, device=dev)
         self.used = 0
         self.forest = _lib.BlkPuctForest(self.B, self.P, self.A, engine.mask_bytes, self.node_cap, self.edge_cap, max_depth,
@@ -72,7 +97,13 @@ class GpuPuct:
                                              "node_edge0", "node_nedge", "node_state", "node_mover", "node_terminal",
                                              "node_term_value", "edge_action", "edge_child", "edge_n", "edge_q", "edge_p",
                                              "root", "path", "path_len", "status", "leaf_node", "leaf_edge", "src_slot",
-                                             "step_action", "scores", "counters", "node_sum_n", "path_node", "node_uniform")])
+                                             "step_action", "scores", "counters", "node_sum_n", "path_node", "node_uniform")],
+                                         t["hash_table"].data_ptr() if self.fused else None, self.hash_cap,
+                                         t["node_hash"].data_ptr() if self.fused else None,
+                                         t["node_tree"].data_ptr() if self.fused else None,
+                                         t["edge_vl"].data_ptr() if self.fused and self.warps_per_tree > 1 else None,
+                                         t["node_front"].data_ptr() if self.fused else None)
+        self._seed = int(getattr(ev, "seed", 0))
         # a net needs the dense bool mask; the uniform prior only needs the legal ids, which the 8x smaller
         # bit-packed mask gives just as well
         self.mask_fmt = "bits" if self.uniform else "bytes"
@@ -95,10 +126,37 @@ class GpuPuct:
             raise _lib.EngineError(f"blk_puct error {rc}: {self._lib.blk_puct_last_error().decode()}")
 
     # ---- roots ------------------------------------------------------------------------------------------
+    def _search_args(self, num_sims: int, cpuct: float = 1.0, epsilon_fix: bool = True):
+        return _lib.BlkPuctSearchArgs(int(num_sims), float(cpuct), int(epsilon_fix), self.pool.data_ptr(), self.warps_per_tree,
+                                      self.playouts_per_leaf, self._seed & 0xFFFFFFFFFFFFFFFF, self.virtual_loss)
+
+    def reroot(self, states: torch.Tensor) -> None:
+        """Fused search only.  The root of tree t becomes the node the tree has filed under the board of ``states[t]``
+        (statistics and subtree kept), or a fresh node: tree reuse the way the reference gets it from a dict that
+        outlives the move (players/mcts_player.py:15-25)."""
+        if not self.fused:
+            raise _lib.EngineError("reroot needs the fused search (board-keyed nodes)")
+        states = states.contiguous()
+        assert states.shape == (self.B, self.eng.state_words) and states.dtype == torch.int32
+        if self.used + self.B > self.node_cap:
+            raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
+        args = self._search_args(0)
+        _lib.check(self._lib.blk_puct_reroot(self.eng._h, C.byref(self.forest), C.byref(args), states.data_ptr(), self._stream()))
+        self.used += self.B
+        self.launches += 1
+
     def set_roots(self, states: torch.Tensor) -> None:
         """Start B fresh trees at ``states`` (int32 [B, state_words])."""
         assert states.shape == (self.B, self.eng.state_words)
         t, B = self.t, self.B
+        if self.fused:
+            t["hash_table"].zero_()
+            t["counters"].zero_()
+            if self.warps_per_tree > 1:
+                t["edge_vl"].zero_()
+            self.used = 0
+            self.reroot(states)
+            return
         self.pool[:B] = states
         self.used = B
         flags, term, _ = self.eng.game_ended(states)
@@ -152,6 +210,8 @@ class GpuPuct:
     def simulate(self, cpuct: float = 1.0, epsilon_fix: bool = True) -> None:
         """One simulation of every tree.  After two eager runs the launch sequence is captured into a CUDA graph
         (one per (cpuct, epsilon_fix)) and replayed: small batches stop being launch-bound."""
+        if self.fused:
+            return self.run(1, cpuct, epsilon_fix)
         if self.used + self.B > self.node_cap:
             raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
         key = (float(cpuct), bool(epsilon_fix))
@@ -175,6 +235,16 @@ class GpuPuct:
         """``simulations`` simulations of every tree.  With ``chain = K > 1`` (and a graph-safe evaluator) K consecutive
         simulations are captured into ONE CUDA graph, so a small forest (the reference's single search,
         players/mcts_player.py:15-22, is B = 1) pays one graph launch per K simulations instead of 3 K kernel launches."""
+        if self.fused:
+            if simulations <= 0:
+                return
+            if self.used + self.B * simulations > self.node_cap:
+                raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
+            args = self._search_args(simulations, cpuct, epsilon_fix)
+            _lib.check(self._lib.blk_puct_search(self.eng._h, C.byref(self.forest), C.byref(args), self._stream()))
+            self.used += self.B * simulations           # upper bound: a simulation creates at most one node per tree
+            self.launches += 1
+            return
         done = 0
         chain = max(1, min(int(chain), simulations))
         if chain > 1 and self.use_cuda_graph:
@@ -204,6 +274,15 @@ class GpuPuct:
     def advance(self, actions: torch.Tensor) -> None:
         """Make the child under ``actions[t]`` the root of tree t (``-1`` leaves a tree where it is)."""
         acts = actions.to(torch.int32).contiguous()
+        if self.fused:
+            # the env transition of the roots under the chosen actions, then the board-keyed lookup: the child the search
+            # built (if it did) becomes the root with its statistics
+            nxt = torch.empty((self.B, self.eng.state_words), dtype=torch.int32, device=self.eng.device)
+            out = self.eng.step(self.root_states(), acts, out_states=nxt, mask=None, want_count=False, want_terminal=False,
+                                want_scores=False)
+            self._last_advance_flags = out.flags
+            self.reroot(nxt)
+            return
         if self.used + self.B > self.node_cap:
             raise _lib.EngineError("GpuPuct state pool exhausted: raise max_simulations")
         self._check(self._lib.blk_puct_advance(C.byref(self.forest), acts.data_ptr(), self._stream()))
@@ -213,6 +292,9 @@ class GpuPuct:
     # ---- results (host side; synchronises) ---------------------------------------------------------------------------
     def check(self) -> None:
         c = self.t["counters"].cpu().numpy()
+        fl = getattr(self, "_last_advance_flags", None)
+        if fl is not None and bool((fl & 2).any()):
+            raise _lib.EngineError("GpuPuct.advance was given an illegal action")
         if c[2]:
             raise _lib.EngineError("GpuPuct capacity overflow (nodes / edges / depth): enlarge the forest")
         if c[3]:

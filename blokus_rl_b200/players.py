@@ -43,14 +43,33 @@ class RandomPlayer(Player):
 
 
 class MCTSPlayer(Player):
-    """``simulations`` PUCT simulations per move, then the most visited action (first maximum)."""
+    """``simulations`` PUCT simulations per move, then the most visited action (first maximum); the tree outlives the
+    move, as the reference's dict does (players/mcts_player.py:15-25).
 
-    def __init__(self, game, evaluator=None, simulations: int = 10, cpuct: float = 1.0):
+    With an evaluator that needs no network (the default :class:`UniformEvaluator` == the reference's DumbNet "mcts"
+    player, compare_arena.py:87-95; or :class:`RolloutEvaluator`) the ONE tree lives on the GPU and a whole move's search
+    is a single launch of the fused search kernel (``blk_puct_search``): ``warps_per_tree = 1`` plays exactly the
+    reference's search (same visit counts), ``warps_per_tree > 1`` is the faster leaf-parallel search with virtual loss
+    (``reference_compat=False`` selects 8 warps).  Network evaluators use the host-side :class:`BatchedMCTS`."""
+
+    def __init__(self, game, evaluator=None, simulations: int = 10, cpuct: float = 1.0, reference_compat: bool = True,
+                 warps_per_tree: int | None = None, max_moves: int = 4 * 21 + 2):
         self.game, self.simulations, self.cpuct = game, simulations, cpuct
         self.evaluator = evaluator or UniformEvaluator()
-        self.search = BatchedMCTS(game.backend.eng, self.evaluator)
-        self.search.trees = [dict()]
-        self._known = {}
+        eng = game.backend.eng
+        on_gpu = getattr(getattr(eng, "device", None), "type", "cpu") == "cuda"
+        fusable = type(self.evaluator).__name__ in ("UniformEvaluator", "RolloutEvaluator")
+        self.gpu = None
+        if on_gpu and fusable:
+            from .gpu_puct import GpuPuct
+            wpt = warps_per_tree if warps_per_tree is not None else (1 if reference_compat else 8)
+            self.gpu = GpuPuct(eng, self.evaluator, num_trees=1, max_simulations=(simulations + 1) * max_moves,
+                               mean_edges_per_node=min(eng.num_actions, 600), warps_per_tree=wpt)
+            self._fresh = True
+        else:
+            self.search = BatchedMCTS(eng, self.evaluator)
+            self.search.trees = [dict()]
+            self._known = {}
 
     def _root(self, s):
         key = s.host_words.tobytes()
@@ -61,6 +80,16 @@ class MCTSPlayer(Player):
         return st
 
     def update_state(self, s, current_player):
+        if self.gpu is not None:
+            if self._fresh:
+                self.gpu.set_roots(s.words)
+                self._fresh = False
+            else:
+                self.gpu.reroot(s.words)
+            self.gpu.run(self.simulations, self.cpuct)
+            action = int(self.gpu.best_actions()[0])
+            self.gpu.check()
+            return self.game.get_next_state(s, current_player, action)
         root = self._root(s)
         for _ in range(self.simulations):
             self.search.simulate([root], self.cpuct)
@@ -68,6 +97,9 @@ class MCTSPlayer(Player):
         return self.game.get_next_state(s, current_player, int(ids[int(np.argmax(dist))]))
 
     def reset(self):
+        if self.gpu is not None:
+            self._fresh = True
+            return
         self.search.reset()
         self.search.trees = [dict()]
         self._known = {}

@@ -39,7 +39,7 @@ extern "C" {
  * (step states out of a pool), blk_rollout_args grew `options`, BLK_OPT_WARP_KERNELS, blk_puct_forest grew `node_uniform`
  * and a 6th counter, blk_puct_expand_args grew `fuse_backup`.  All additions are trailing fields: zero-initialised structs keep
  * their version-1 meaning.
- * 3 = blk_puct_forest grew the board-keyed node table (hash_table, hash_capacity, node_hash, node_tree) and edge_vl;
+ * 3 = blk_puct_forest grew the board-keyed node table (hash_table, hash_capacity, node_hash, node_tree), edge_vl and node_front;
  * blk_puct_search / blk_puct_reroot (whole simulations inside one kernel); work-queue slots are per stream / per graph capture;
  * every entry point restores the caller's current device. */
 #define BLK_ABI_VERSION 3
@@ -209,6 +209,8 @@ typedef struct {
     uint64_t *node_hash;          /* [nodes] 64-bit hash of (tree, board rows) */
     int32_t *node_tree;           /* [nodes] tree the node belongs to (equal boards of different trees stay apart) */
     int32_t *edge_vl;             /* [edges] virtual-loss counters, zeroed by the caller (leaf-parallel search only) */
+    int32_t *node_front;          /* [nodes] blk_puct_search: edges [0, front) of the node have been selected at least once (with
+                                     the uniform prior the selected edges always form a prefix; see csrc/blk_search.cuh) */
 } blk_puct_forest;
 
 typedef struct {
@@ -262,7 +264,10 @@ int blk_puct_advance(const blk_puct_forest *f, const int32_t *actions, void *str
 
 /* MCTS.simulate x num_sims for every tree, selection, env transition, legal-move expansion and backup fused in one
  * kernel (one warp, or `warps_per_tree` warps, per tree); nodes are keyed by board cells like the reference's dict
- * (mcts.py:37), a simulation that reaches a known board continues its descent there.  Needs the engine (env tables). */
+ * (mcts.py:37), a simulation that reaches a known board continues its descent there.  Needs the engine (env tables).
+ * A forest searched this way is built by blk_puct_reroot / blk_puct_search only (node i keeps its state in pool slot i;
+ * counters[0] = nodes, counters[1] = edges; zero the counters and hash_table to start over); do not mix it with the
+ * lockstep kernels above. */
 int blk_puct_search(blk_engine *h, const blk_puct_forest *f, const blk_puct_search_args *args, void *stream);
 /* Tree reuse the way the reference gets it (its dict outlives the move: players/mcts_player.py:15-25): the root of tree t
  * becomes the node filed under the board of states[t] if the tree has one, else a fresh unexpanded node. */

@@ -33,9 +33,27 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_abi_version_and_struct_sizes(lib):
     from blokus_rl_b200 import _lib
-    assert lib.blk_abi_version() == 2
+    assert lib.blk_abi_version() == 3
     assert C.sizeof(_lib.BlkConfig) == 16 and C.sizeof(_lib.BlkInfo) == 44
     assert C.sizeof(_lib.BlkStepArgs) == 128 and C.sizeof(_lib.BlkRolloutArgs) == 112
+
+
+def test_ctypes_structs_have_the_c_layout(tmp_path):
+    """Every struct of include/blokus_b200.h: sizeof and the offset of its last field as gcc lays them out == ctypes'."""
+    import subprocess
+    from blokus_rl_b200 import _lib
+    pairs = [("blk_config", _lib.BlkConfig, "device"), ("blk_info", _lib.BlkInfo, "sm_count"),
+             ("blk_step_args", _lib.BlkStepArgs, "state_index"), ("blk_rollout_args", _lib.BlkRolloutArgs, "options"),
+             ("blk_puct_forest", _lib.BlkPuctForest, "node_front"), ("blk_puct_expand_args", _lib.BlkPuctExpandArgs, "fuse_backup"),
+             ("blk_puct_search_args", _lib.BlkPuctSearchArgs, "virtual_loss")]
+    body = "".join(f'printf("%zu %zu\\n", sizeof({c}), offsetof({c}, {last}));' for c, _, last in pairs)
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "blokus_b200.h"\nint main(void){' + body + "return 0;}")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-I", str(ROOT / "include"), str(src), "-o", str(exe)])
+    got = [tuple(int(x) for x in ln.split()) for ln in subprocess.check_output([str(exe)], text=True).splitlines()]
+    want = [(C.sizeof(t), getattr(t, last).offset) for _, t, last in pairs]
+    assert got == want
 
 
 def test_no_cpu_fallback(lib):

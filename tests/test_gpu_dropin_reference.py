@@ -120,3 +120,28 @@ def test_reference_mcts_over_the_gpu_engine_reproduces_its_golden_vectors(chdir_
         assert np.allclose([float(e[2]) for e in node], c["Q"], rtol=0, atol=1e-12)
         done += 1
     assert done >= 6
+
+
+def test_gpu_mcts_player_plays_the_reference_mcts_players_moves(chdir_tmp):
+    """players/mcts_player.py (unmodified, persistent dict, DumbNet-like uniform net) against this repo's MCTSPlayer, whose
+    single tree lives on the GPU (fused search kernel, board-keyed nodes, reroot between moves): same moves, whole game."""
+    from blokus_rl_b200.backend import EngineBackend
+    from blokus_rl_b200.game_wrapper import BlokusGameWrapper
+    from blokus_rl_b200.players import MCTSPlayer
+    b = EngineBackend(7, 2)
+    ref = _reference_over(b, chdir_tmp, 7, 2)
+    ours = BlokusGameWrapper(board_size=7, number_of_players=2, backend=b)
+    sims = 40
+    ref_players = [ref.MCTSPlayer(ref.game, UniformNet(2), sims) for _ in range(2)]
+    our_players = [MCTSPlayer(ours, simulations=sims) for _ in range(2)]
+    assert all(p.gpu is not None and p.gpu.fused for p in our_players)
+    s_ref, cur = ref.game.get_init_board()
+    s_our, cur_our = ours.get_init_board()
+    plies = 0
+    while ref.game.get_game_ended(s_ref) is None:
+        s_ref, nxt = ref_players[cur].update_state(s_ref, cur)
+        s_our, nxt_our = our_players[cur].update_state(s_our, cur)
+        assert nxt == nxt_our and (s_ref[0].board_contents == b.board_contents(s_our)).all(), f"ply {plies}: different move"
+        cur = nxt
+        plies += 1
+    assert plies >= 6 and ours.get_game_ended(s_our) is not None
