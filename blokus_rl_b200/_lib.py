@@ -120,7 +120,7 @@ def load() -> C.CDLL:
     lib.blk_puct_advance.argtypes = [C.POINTER(BlkPuctForest), C.c_void_p, C.c_void_p]
     lib.blk_puct_search.argtypes = [C.c_void_p, C.POINTER(BlkPuctForest), C.POINTER(BlkPuctSearchArgs), C.c_void_p]
     lib.blk_puct_reroot.argtypes = [C.c_void_p, C.POINTER(BlkPuctForest), C.POINTER(BlkPuctSearchArgs), C.c_void_p, C.c_void_p]
-    if lib.blk_abi_version() != ABI_VERSION:
+    if lib.blk_abi_version() != ABI_VERSION and not _os.environ.get("BLOKUS_B200_ANY_ABI"):   # (A/B runs against an older build)
         raise EngineError("libblokus_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -34,7 +34,17 @@ def kernel_source_hash() -> str:
     return h.hexdigest()[:16]
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None) -> Path:
+def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None, out: Path | None = None) -> Path:
+    """``out``: build a VARIANT library there (own object directory next to it) -- A/B runs of the compile-time knobs
+    (BLK_WARPS, BLK_ROLL_WARPS, ...) select it at run time with BLOKUS_B200_LIB; the product library is untouched."""
+    global OUT, OBJ
+    if out is not None:
+        saved = (OUT, OBJ)
+        OUT, OBJ = Path(out), Path(out).with_suffix(".objs")
+        try:
+            return build(True, verbose, extra_flags)
+        finally:
+            OUT, OBJ = saved
     if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
         return OUT
     OBJ.mkdir(exist_ok=True)

@@ -49,6 +49,9 @@ constexpr uint32_t kAllLanes = 0xffffffffu;
 #else
 #define BLK_STORE16(p, v) __stcg((p), (v))
 #endif
+#ifndef BLK_GUARDED_FIELD_STORES
+#define BLK_GUARDED_FIELD_STORES 0   // 1: bounds-tested field stores in eval_fields (the round-1 form); 0: unconditional, in program order
+#endif
 #ifndef BLK_EMIT_UNROLL
 #define BLK_EMIT_UNROLL 6
 #endif
@@ -163,6 +166,12 @@ __device__ __forceinline__ int kth_set_bit(uint32_t w, int k) {
         if (k >= c) { k -= c; pos += s; }
     }
     return pos;
+}
+// The same for a WARP-UNIFORM (w, k), all lanes calling: lane i tests bit i (a binary search is 5 dependent rounds of
+// shift / mask / popc / compare / select; this is one round plus a ballot).
+__device__ __forceinline__ int kth_set_bit_warp(uint32_t w, int k, int lane) {
+    const bool hit = ((w >> lane) & 1u) && __popc(w & ((1u << lane) - 1u)) == k;
+    return __ffs(__ballot_sync(kAllLanes, hit)) - 1;
 }
 
 // PTX shl clamps shift amounts above 31 to 32 (result 0); C's << would be undefined there.
@@ -347,12 +356,30 @@ __device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint
             ds[r][x] = (r + x <= 4) ? (d >> x) : 0u;
         }
     }
+    // No bounds test on the stores below.  A lane whose anchor row lets the footprint stick out at the bottom
+    // (lane > N - h) ANDs in a row >= N, which is 0, so it computes f_ = 0 -- and its slot fld[o * (N + 1) - hsum + lane]
+    // lies behind orientation o's own rows: in the slots of the FOLLOWING orientations, whose own lanes store there later
+    // (used pieces store their zeros just the same), or, behind the last orientation, in the zero padding / the 32
+    // scratch words after the fields.  A warp's shared-memory stores execute in program order, and `volatile` keeps the
+    // compiler from reordering them, so the later, real value always wins.  With a bounds test per store the compiler
+    // turned the last orientation of every piece into a divergent branch: a compare plus a BSSY / BSYNC / BRA triple per
+    // piece, 90+ warp instructions per evaluation.
+#if BLK_GUARDED_FIELD_STORES
+    uint32_t *fldp = fld + lane;
     bool ok[6];
 #pragma unroll
     for (int h = 1; h <= 5; ++h) ok[h] = lane <= N - h;
+#define BLK_FLD_ST(idx, v, h) if (ok[h]) fldp[idx] = (v)
+#else
+    volatile uint32_t *fldp = fld + lane;
+#define BLK_FLD_ST(idx, v, h) fldp[idx] = (v)
+#endif
+    // the inventory is the same in every lane, but only a value that comes out of a warp-wide reduction is KNOWN to be
+    // uniform: REDUX leaves it in a uniform register, and the 21 per-piece branches below become plain uniform branches
+    // without a reconvergence pair (BSSY / BSYNC) around each
+    invc = __reduce_or_sync(kAllLanes, invc);
     uint32_t anyacc = 0u;
     const int np1 = N + 1;
-    uint32_t *fldp = fld + lane;
     // AND / OR over the cells of five base trominoes, shared by the 75 footprints that contain one of them
     uint32_t base_and[5], base_or[5];
 #define BLK_BASE(b, y0, x0, y1, x1, y2, x2)                  \
@@ -362,7 +389,7 @@ __device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint
     {                                                                                                  \
         const uint32_t f_ = (base_and[b] & fs[y0][x0] & fs[y1][x1]) & (base_or[b] | ds[y0][x0] | ds[y1][x1]); \
         if (kAny) anyacc |= f_;                                                                        \
-        if (kStage && ok[h]) fldp[(o) * np1 - (hsum)] = f_;                                            \
+        if (kStage) BLK_FLD_ST((o) * np1 - (hsum), f_, h);                                             \
     }
 #define BLK_PIECE_BEGIN(p) if ((invc >> (p)) & 1u) {
 #define BLK_ORIENT(o, p, h, w, n, hsum, y0, x0, y1, x1, y2, x2, y3, x3, y4, x4)                        \
@@ -370,13 +397,12 @@ __device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint
         const uint32_t f_ = (fs[y0][x0] & fs[y1][x1] & fs[y2][x2] & fs[y3][x3] & fs[y4][x4]) &         \
                             (ds[y0][x0] | ds[y1][x1] | ds[y2][x2] | ds[y3][x3] | ds[y4][x4]);         \
         if (kAny) anyacc |= f_;                                                                        \
-        if (kStage && ok[h]) fldp[(o) * np1 - (hsum)] = f_;                                            \
+        if (kStage) BLK_FLD_ST((o) * np1 - (hsum), f_, h);                                             \
     }
 #define BLK_PIECE_ELSE(p) \
     }                     \
     else if (kStage) {
-#define BLK_ZERO(o, h, hsum) \
-    if (ok[h]) fldp[(o) * np1 - (hsum)] = 0u;
+#define BLK_ZERO(o, h, hsum) BLK_FLD_ST((o) * np1 - (hsum), 0u, h);
 #define BLK_PIECE_END(p) }
 #include "blk_orient.inc"
 #undef BLK_BASE
@@ -386,6 +412,7 @@ __device__ __forceinline__ uint32_t eval_fields(uint32_t fr0, uint32_t dg0, uint
 #undef BLK_PIECE_ELSE
 #undef BLK_ZERO
 #undef BLK_PIECE_END
+#undef BLK_FLD_ST
     return anyacc;
 }
 
@@ -409,7 +436,7 @@ __device__ __forceinline__ uint32_t assemble_word(int g, const uint32_t *fld, co
 __device__ __forceinline__ uint32_t assemble_word3(int g, const uint32_t *fld, const uint2 *wdesc) {
     const uint2 d = wdesc[g];
     const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(fld) + d.x);
-    return (p[0] >> (d.y & 31u)) | shl_clamp(p[1], __byte_perm(d.y, 0u, 0x4441u)) |
+    return __funnelshift_r(p[0], 0u, d.y) | shl_clamp(p[1], __byte_perm(d.y, 0u, 0x4441u)) |
            shl_clamp(p[2], __byte_perm(d.y, 0u, 0x4442u));
 }
 
@@ -773,7 +800,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                 const int J = __ffs(__ballot_sync(kAllLanes, k < incl2)) - 1;
                 k -= __shfl_sync(kAllLanes, incl2 - c2, J);
                 const uint32_t wsel = __shfl_sync(kAllLanes, word, J);
-                pick = (((R << 5) + J) << 5) + kth_set_bit(wsel, k);
+                pick = (((R << 5) + J) << 5) + kth_set_bit_warp(wsel, k, lane);
             }
             if (lane == 0) a.next_action[env] = pick;
         }
@@ -867,25 +894,23 @@ __device__ __forceinline__ int playout_game(EnvRegs &e, const SmemTables &tb, co
         int k = static_cast<int>(__umulhi(philox_word(rnd, ply), static_cast<uint32_t>(cnt)));
         const int L = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
         k -= __shfl_sync(kAllLanes, incl - mine, L);
-        // second level: the chunk of lane L, 32 fields at a time
+        // second level: the chunk of lane L (at most 53 fields: two halves of 32).  Both halves' popcounts ride through
+        // ONE warp scan as a packed pair (counts are far below 2^16), instead of a loop with a scan per half.
         const int chunk = kN == 20 ? 52 : per;
         const int chunk_len = kN == 20 ? (L == 31 ? 53 : 52) : per;
-        int fsel = -1, kk = 0;
-        for (int half = 0; half * 32 < chunk_len; ++half) {
-            const int j = half * 32 + lane;
-            const int i = L * chunk + j;
-            const int c = (j < chunk_len && i < nf) ? __popc(fld[i]) : 0;
-            const int inc2 = warp_incl_scan(c, lane);
-            const uint32_t b = __ballot_sync(kAllLanes, k < inc2);
-            if (b) {
-                const int J = __ffs(b) - 1;
-                kk = k - __shfl_sync(kAllLanes, inc2 - c, J);
-                fsel = L * chunk + half * 32 + J;
-                break;
-            }
-            k -= __shfl_sync(kAllLanes, inc2, 31);
-        }
-        const int bit = kth_set_bit(fld[fsel], kk);
+        const int i_lo = L * chunk + lane, i_hi = i_lo + 32;
+        const int c_lo = (lane < chunk_len && i_lo < nf) ? __popc(fld[i_lo]) : 0;
+        const int c_hi = (lane + 32 < chunk_len && i_hi < nf) ? __popc(fld[i_hi]) : 0;
+        const int inc2 = warp_incl_scan(c_lo | (c_hi << 16), lane);
+        const int tot_lo = __shfl_sync(kAllLanes, inc2, 31) & 0xffff;
+        const bool upper = k >= tot_lo;
+        if (upper) k -= tot_lo;
+        const int c = upper ? c_hi : c_lo;
+        const int inc = upper ? (inc2 >> 16) : (inc2 & 0xffff);
+        const int J = __ffs(__ballot_sync(kAllLanes, k < inc)) - 1;
+        const int kk = k - __shfl_sync(kAllLanes, inc - c, J);
+        const int fsel = L * chunk + (upper ? 32 : 0) + J;
+        const int bit = kth_set_bit_warp(fld[fsel], kk, lane);
         if (log != nullptr && lane == 0 && nply < log_cap - 1) log[nply] = static_cast<uint16_t>(tb.foff[fsel] + bit);
         uint32_t pm; int piece, ncells;
         decode_field(fsel, bit, tb, lane, pm, piece, ncells);

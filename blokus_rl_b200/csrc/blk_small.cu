@@ -136,7 +136,7 @@ __device__ __forceinline__ int small_score(const uint32_t *st, int q, int P, int
 
 // kN only makes the three per-size translation units instantiate distinct symbols
 template <int kN, int kP, int kFmt, bool kSample>
-__global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, kP == 2 ? 2 : 3) small_step_kernel(const SmallParams sp) {
+__global__ void __launch_bounds__(kP == 2 ? kST2 : kST4, kP == 2 ? 512 / kST2 : 384 / kST4) small_step_kernel(const SmallParams sp) {
     static_assert(kN == kSN, "one translation unit per board size");
     constexpr int T = kP == 2 ? kST2 : kST4;        // envs (slots) per block and pass
     constexpr int N = kSN, P = kP;
