@@ -75,3 +75,22 @@ def test_arena_gpu(engine7, engine20):
     scores, terminal, _ = play_match_batched(engine20, [RolloutSeat(8), RandomSeat(), RandomSeat(), RandomSeat()], games_num=16, seed=2)
     assert (np.abs(terminal).sum(1) > 0).all()
     assert scores[0] > scores[1:].mean()          # playouts beat uniform-random play
+
+
+@pytest.mark.gpu
+def test_sharded_self_play_is_partition_invariant(engine7):
+    """Self-play games shard by GAME index (alphazero/trainer.py:152-154 plays them one after the other): game g draws its
+    moves from its own generator and searches its own tree, so 3 ranks' games are the single rank's games."""
+    from blokus_rl_b200.distributed import SELFPLAY_COUNTERS, Shard, self_play_shard
+    whole_c, whole = self_play_shard(engine7, Shard(0, 1, 9), num_mcts_sims=8, seed=5)
+    parts = [self_play_shard(engine7, Shard(r, 3, 9), num_mcts_sims=8, seed=5) for r in range(3)]
+    games = [g for _, data in parts for g in data]
+    assert len(games) == len(whole) == 9
+    for a, b in zip(games, whole):
+        assert len(a) == len(b)
+        for (oa, ma, pa, sa), (ob, mb, pb, sb) in zip(a, b):
+            assert (oa == ob).all() and (ma == mb).all() and (pa == pb).all() and (sa == sb).all()
+    total = sum(c for c, _ in parts)
+    whole_d, total_d = dict(zip(SELFPLAY_COUNTERS, whole_c.tolist())), dict(zip(SELFPLAY_COUNTERS, total.tolist()))
+    assert total_d["games"] == 9 and total_d["examples"] == whole_d["examples"]
+    assert [total_d[f"wins_p{q}"] for q in range(2)] == [whole_d[f"wins_p{q}"] for q in range(2)]
