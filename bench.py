@@ -748,10 +748,9 @@ def extra_workloads(eng, torch):
         env.reset()
         rng = np.random.default_rng(0)
 
-        def agent_step():
-            flat, cnt = env.legal_id_arrays()
-            starts = np.cumsum(cnt) - cnt
-            acts = flat[starts + (rng.random(E) * cnt).astype(np.int64)]
+        def agent_step():                           # a vectorised random masked policy on the host
+            ids, cnt = env.legal_ids_padded()
+            acts = ids[np.arange(E), (rng.random(E) * cnt).astype(np.int64)].astype(np.int64)
             env.step(acts)
         for _ in range(5):
             agent_step()

@@ -71,6 +71,8 @@ class BlokusVectorEnv:
         self._ids_host = None              # (counts, ids) of the current states on the host, filled on demand
         self._h_board, self._h_reward = self._host((num_envs, self.N, self.N), torch.uint8), self._host(num_envs, torch.float32)
         self._h_done = self._host(num_envs, torch.bool)
+        self._h_fret, self._h_flen = self._host(num_envs, torch.float32), self._host(num_envs, torch.int64)
+        self._h_fobs = self._host((num_envs, self.N, self.N), torch.uint8)
 
     def _alloc_idx(self):
         E, dev = self.num_envs, self.eng.device
@@ -167,34 +169,42 @@ class BlokusVectorEnv:
     def step(self, actions):
         acts = torch.as_tensor(np.asarray(actions), dtype=torch.int32).to(self.eng.device, non_blocking=True)
         obs, reward, done, (fin_ret, fin_len, final_obs) = self.step_device(acts)
-        # one round trip: board cells, rewards, done flags and the agent's next legal ids travel together
-        self._h_board.copy_(obs, non_blocking=True)
-        self._h_reward.copy_(reward, non_blocking=True)
-        self._h_done.copy_(done, non_blocking=True)
+        # one round trip: board cells, rewards, done flags, episode statistics and the agent's next legal ids travel together
+        for dst, src in ((self._h_board, obs), (self._h_reward, reward), (self._h_done, done), (self._h_fret, fin_ret),
+                         (self._h_flen, fin_len), (self._h_fobs, final_obs)):
+            dst.copy_(src, non_blocking=True)
         self._launch_ids()
         self._sync()
         self._collect_ids()
         done_h = self._h_done.numpy().copy()
         info = {}
-        if done_h.any():
-            r, l = fin_ret.cpu().numpy(), fin_len.cpu().numpy()
-            fo = final_obs.cpu().numpy().astype(np.float32)
-            info["final_info"] = np.array([{"episode": {"r": float(r[i]), "l": int(l[i])}} if done_h[i] else None
-                                           for i in range(self.num_envs)], dtype=object)
-            info["final_observation"] = np.array([fo[i] if done_h[i] else None for i in range(self.num_envs)],
-                                                 dtype=object)
-            info["_final_info"] = done_h.copy()
+        idx = np.flatnonzero(done_h)
+        if len(idx):                                       # gymnasium-0.29 autoreset bookkeeping, only for the envs that finished
+            r, l, fo = self._h_fret.numpy(), self._h_flen.numpy(), self._h_fobs.numpy()
+            final_info = np.full(self.num_envs, None, dtype=object)
+            final_obs_h = np.full(self.num_envs, None, dtype=object)
+            for i in idx:
+                final_info[i] = {"episode": {"r": float(r[i]), "l": int(l[i])}}
+                final_obs_h[i] = fo[i].astype(np.float32)
+            info = {"final_info": final_info, "final_observation": final_obs_h, "_final_info": done_h.copy()}
         return (self._h_board.numpy().astype(np.float32), self._h_reward.numpy().copy(), done_h,
                 np.zeros(self.num_envs, dtype=bool), info)
 
-    def legal_id_arrays(self):
-        """The agent's legal action ids per env as int64 arrays (views of one flat array): what
-        ``mask[i, possible_move] = 1`` indexes with (ppo/agent.py:36-37), without building Python lists."""
+    def legal_ids_padded(self):
+        """The agent's legal action ids as they come off the device: ``(ids uint16 [num_envs, width], counts int32
+        [num_envs])``, row i valid up to ``counts[i]``, ascending.  Views of the pinned staging buffers (valid until the next
+        ``step`` / ``reset``): the form a vectorised consumer wants."""
         if self._ids_host is None:
             self._launch_ids()
             self._sync()
             self._collect_ids()
         cnt, ids = self._ids_host
+        return ids, cnt
+
+    def legal_id_arrays(self):
+        """The agent's legal action ids per env as int64 arrays (views of one flat array): what
+        ``mask[i, possible_move] = 1`` indexes with (ppo/agent.py:36-37), without building Python lists."""
+        ids, cnt = self.legal_ids_padded()
         keep = np.arange(ids.shape[1], dtype=np.int32)[None, :] < cnt[:, None]
         return ids[keep].astype(np.int64), cnt
 
