@@ -789,6 +789,37 @@ def extra_workloads(eng, torch):
         search.check()
         extra[name] = B * sims / sec
         del search
+    # configs[3]: AlphaZero self-play (config/alphazero_blokus_20x20.yml: 25 simulations per move) -- lockstep forest, fused leaf
+    # expansion (state + mask + observation planes in one launch) feeding a torch net of the reference's ResNet shape
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("selfplay_bench", ROOT / "tools" / "selfplay_bench.py")
+        sb = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(sb)
+        from blokus_rl_b200.mcts import TorchNetEvaluator
+        games, sims, plies = 256, 25, 3
+        net = sb.PolicyValueNet().to(eng.device).eval()
+        search = GpuPuct(eng, TorchNetEvaluator(net), num_trees=games, max_simulations=(sims + 1) * (plies + 3) + 2, mean_edges_per_node=400)
+        search.set_roots(eng.new_states(games))
+
+        def one_move():
+            search.run(sims)
+            search.advance(search.best_actions_device())
+        one_move()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(plies):
+            one_move()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        search.check()
+        extra["selfplay_resnet_simulations_per_s_256_games"] = games * plies * sims / dt
+        extra["selfplay_resnet_plies_per_s_256_games"] = games * plies / dt
+        extra["selfplay_workload"] = ("256 concurrent self-play games, 25 simulations per move, random-init torch net of the reference's ResNet "
+                                      "shape (24.7 M parameters, fp32), leaves expanded by blk_step with fused observation planes; net-bound")
+        del search, net
+    except Exception as e:                      # noqa: BLE001 - an extra, never a reason to lose the bench line
+        extra["selfplay_error"] = repr(e)[:200]
     extra["mcts_workload"] = ("B PUCT searches from 24-ply roots, uniform prior (DumbNet), trees on the GPU.  mcts_simulations_per_s: "
                               "4096 trees in lockstep, 3 launches per simulation (blk_puct_select / blk_step / blk_puct_expand) -- the "
                               "path a torch net uses; *_fused_*, *_B1/B4/B16: whole simulations inside one kernel (blk_puct_search), a "
