@@ -575,6 +575,49 @@ __device__ __forceinline__ void emit_observation(const EnvRegs &e, float *__rest
     }
 }
 
+// ---- the legal set read straight from the staged fields (field order is action-id order) ----
+// Every lane owns a contiguous chunk of fields (52 at N = 20, lane 31 one more); returns this lane's number of legal actions.
+template <int kN>
+__device__ __forceinline__ int count_field_chunk(const uint32_t *fld, int nf, int per, int lane) {
+    int mine = 0;
+    if (kN == 20) {                 // 1665 fields = 32 x 52 (+1 for lane 31): 13 conflict-free LDS.128 per lane
+        const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 13 * lane;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+            const uint4 x = f4[j];
+            mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+        }
+        if (lane == 31) mine += __popc(fld[1664]);
+    } else {
+        for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
+    }
+    return mine;
+}
+// The k-th legal action (0-based, ascending id) given every lane's chunk count `mine` and their inclusive scan `incl`:
+// returns the field, `bit` = the anchor column inside it.  First level: which lane's chunk; second level: which field of
+// that chunk (at most 53: two halves of 32 whose popcounts ride through ONE warp scan as a packed 16 + 16 bit pair).
+template <int kN>
+__device__ __forceinline__ int kth_legal_field(const uint32_t *fld, int k, int mine, int incl, int nf, int per, int lane, int &bit) {
+    const int L = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
+    k -= __shfl_sync(kAllLanes, incl - mine, L);
+    const int chunk = kN == 20 ? 52 : per;
+    const int chunk_len = kN == 20 ? (L == 31 ? 53 : 52) : per;
+    const int i_lo = L * chunk + lane, i_hi = i_lo + 32;
+    const int c_lo = (lane < chunk_len && i_lo < nf) ? __popc(fld[i_lo]) : 0;
+    const int c_hi = (lane + 32 < chunk_len && i_hi < nf) ? __popc(fld[i_hi]) : 0;
+    const int inc2 = warp_incl_scan(c_lo | (c_hi << 16), lane);
+    const int tot_lo = __shfl_sync(kAllLanes, inc2, 31) & 0xffff;
+    const bool upper = k >= tot_lo;
+    if (upper) k -= tot_lo;
+    const int c = upper ? c_hi : c_lo;
+    const int inc = upper ? (inc2 >> 16) : (inc2 & 0xffff);
+    const int J = __ffs(__ballot_sync(kAllLanes, k < inc)) - 1;
+    const int kk = k - __shfl_sync(kAllLanes, inc - c, J);
+    const int fsel = L * chunk + (upper ? 32 : 0) + J;
+    bit = kth_set_bit_warp(fld[fsel], kk, lane);
+    return fsel;
+}
+
 // ---------------------------------------------------------------------------------------------
 // step / legal-mask kernel
 // ---------------------------------------------------------------------------------------------
@@ -692,14 +735,51 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
 
         // ---- gather the action-id-ordered mask from the staged fields and stream it out ----
         int cnt = 0;
-        if (kFmt != 0 || kSample || want_count) {
+        int idx_pick = -1;
+        if (kFmt == 4) {
+            // Index list: the ids come straight out of the fields (field order is id order), no mask words are built.
+            // Every lane counts its contiguous chunk of fields, a scan gives it its first slot, and it writes its ids there.
+            // (The mask-word route -- 30 passes of gather + scan + per-lane bit loops -- cost 4,500 warp instructions per env.)
+            const int nf_ = kN == 20 ? 1665 : gg.nf;
+            const int per = (nf_ + 31) >> 5;
+            const int mine = count_field_chunk<kN>(fld, nf_, per, lane);
+            const int incl = warp_incl_scan(mine, lane);
+            cnt = __shfl_sync(kAllLanes, incl, 31);
+            uint16_t *irow = reinterpret_cast<uint16_t *>(a.mask) + env * mstride;
+            int pos = incl - mine;
+            const int chunk = kN == 20 ? 52 : per;
+            const int i0 = lane * chunk;
+            const int len = kN == 20 ? (lane == 31 ? 53 : 52) : per;
+            if (mine > 0) {
+                for (int t = 0; t < len; ++t) {
+                    const int i = i0 + t;
+                    uint32_t w = i < nf_ ? fld[i] : 0u;
+                    if (w) {
+                        const int base = tb.foff[i];
+                        do {
+                            if (pos < mstride) irow[pos] = static_cast<uint16_t>(base + __ffs(w) - 1);
+                            ++pos;
+                            w &= w - 1;
+                        } while (w);
+                    }
+                }
+            }
+            __syncwarp();
+            if (cnt > mstride) flags |= BLK_FLAG_TRUNCATED;
+            if (kSample && cnt > 0) {
+                const uint32_t ply = e.meta >> 16;
+                const uint32_t u = philox_word(philox4(ply >> 2, e.game, 0u, 0u, static_cast<uint32_t>(a.seed),
+                                                       static_cast<uint32_t>(a.seed >> 32) ^ (a.env_id_base + static_cast<uint32_t>(env))), ply);
+                int bit;
+                const int fsel = kth_legal_field<kN>(fld, static_cast<int>(__umulhi(u, static_cast<uint32_t>(cnt))), mine, incl, nf_, per, lane, bit);
+                idx_pick = static_cast<int>(tb.foff[fsel]) + bit;
+            }
+        } else if (kFmt != 0 || kSample || want_count) {
             unsigned char *row = reinterpret_cast<unsigned char *>(a.mask) + env * mstride + 16 * lane;
             uint32_t *wrow = reinterpret_cast<uint32_t *>(a.mask) + env * mstride + lane;
             unsigned char *urow = reinterpret_cast<unsigned char *>(a.mask) + env * mstride;     // kFmt == 3 only
             const int ush = static_cast<int>(reinterpret_cast<uintptr_t>(urow) & 15);
             uint32_t uprev = 0u;
-            uint16_t *irow = reinterpret_cast<uint16_t *>(a.mask) + env * mstride;                // kFmt == 4 only
-            int ibase = 0;
 #pragma unroll(kEmitUnroll)
             for (int r = 0; r < (kN == 20 ? 30 : rounds); ++r) {
                 uint32_t word;
@@ -714,20 +794,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                     cnt += pc;
                 }
                 if (kFmt == 4) {
-                    // sparse form: ids of the set bits in ascending order.  Lane l's word precedes lane l+1's, so an
-                    // exclusive scan of the per-lane popcounts gives every lane its slot range in this pass.
-                    if (__any_sync(kAllLanes, pc != 0)) {          // most 1,024-bit passes of a 0.6 % dense mask are empty
-                        const int incl = warp_incl_scan(pc, lane);
-                        int slot = ibase + incl - pc;
-                        uint32_t w = word;
-                        while (w) {
-                            const int id = (((r << 5) + lane) << 5) + __ffs(w) - 1;
-                            w &= w - 1;
-                            if (slot < mstride) irow[slot] = static_cast<uint16_t>(id);
-                            ++slot;
-                        }
-                        ibase += __shfl_sync(kAllLanes, incl, 31);
-                    }
+                    // (handled above, straight from the fields)
                 } else if (kFmt == 1) {
                     if (r < (kN == 20 ? 29 : rounds - 1) || (r << 5) + lane < mw) wrow[r << 5] = word;
                 } else if (kFmt == 2) {
@@ -772,14 +839,13 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                 }
             }
             if (!kSample) cnt = warp_sum(cnt);
-            if (kFmt == 4 && cnt > mstride) flags |= BLK_FLAG_TRUNCATED;
         }
         if (want_count && lane == 0) a.legal_count[env] = cnt;
 
         // ---- uniform random legal action for the new mover: k = mulhi(u32, n), k-th set bit ascending ----
         if (kSample) {
-            int pick = -1;
-            if (cnt > 0) {
+            int pick = idx_pick;
+            if (kFmt != 4 && cnt > 0) {
                 __syncwarp();
                 const uint32_t ply = e.meta >> 16;
                 const uint32_t u = philox_word(philox4(ply >> 2, e.game, 0u, 0u, static_cast<uint32_t>(a.seed),
@@ -860,17 +926,7 @@ __device__ __forceinline__ int playout_game(EnvRegs &e, const SmemTables &tb, co
             __syncwarp();
             // count legal actions: lane sums popcounts over its contiguous chunk of fields (field order = id order);
             // "has a move" falls out of the count, so the fields are not OR-reduced separately
-            if (kN == 20) {                 // 1665 fields = 32 x 52 (+1 for lane 31): 13 conflict-free LDS.128 per lane
-                const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 13 * lane;
-#pragma unroll
-                for (int j = 0; j < 13; ++j) {
-                    const uint4 x = f4[j];
-                    mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
-                }
-                if (lane == 31) mine += __popc(fld[1664]);
-            } else {
-                for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
-            }
+            mine = count_field_chunk<kN>(fld, nf, per, lane);
             incl = warp_incl_scan(mine, lane);
             has = __shfl_sync(kAllLanes, incl, 31) > 0;
             // a player without a move never gets one back (others only take cells away, and it places nothing
@@ -891,26 +947,9 @@ __device__ __forceinline__ int playout_game(EnvRegs &e, const SmemTables &tb, co
             rnd = philox4(ply >> 2, e.game, stream, 0u, key0, key1);
             rnd_block = static_cast<int>(ply >> 2);
         }
-        int k = static_cast<int>(__umulhi(philox_word(rnd, ply), static_cast<uint32_t>(cnt)));
-        const int L = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
-        k -= __shfl_sync(kAllLanes, incl - mine, L);
-        // second level: the chunk of lane L (at most 53 fields: two halves of 32).  Both halves' popcounts ride through
-        // ONE warp scan as a packed pair (counts are far below 2^16), instead of a loop with a scan per half.
-        const int chunk = kN == 20 ? 52 : per;
-        const int chunk_len = kN == 20 ? (L == 31 ? 53 : 52) : per;
-        const int i_lo = L * chunk + lane, i_hi = i_lo + 32;
-        const int c_lo = (lane < chunk_len && i_lo < nf) ? __popc(fld[i_lo]) : 0;
-        const int c_hi = (lane + 32 < chunk_len && i_hi < nf) ? __popc(fld[i_hi]) : 0;
-        const int inc2 = warp_incl_scan(c_lo | (c_hi << 16), lane);
-        const int tot_lo = __shfl_sync(kAllLanes, inc2, 31) & 0xffff;
-        const bool upper = k >= tot_lo;
-        if (upper) k -= tot_lo;
-        const int c = upper ? c_hi : c_lo;
-        const int inc = upper ? (inc2 >> 16) : (inc2 & 0xffff);
-        const int J = __ffs(__ballot_sync(kAllLanes, k < inc)) - 1;
-        const int kk = k - __shfl_sync(kAllLanes, inc - c, J);
-        const int fsel = L * chunk + (upper ? 32 : 0) + J;
-        const int bit = kth_set_bit_warp(fld[fsel], kk, lane);
+        const int k = static_cast<int>(__umulhi(philox_word(rnd, ply), static_cast<uint32_t>(cnt)));
+        int bit;
+        const int fsel = kth_legal_field<kN>(fld, k, mine, incl, nf, per, lane, bit);
         if (log != nullptr && lane == 0 && nply < log_cap - 1) log[nply] = static_cast<uint16_t>(tb.foff[fsel] + bit);
         uint32_t pm; int piece, ncells;
         decode_field(fsel, bit, tb, lane, pm, piece, ncells);

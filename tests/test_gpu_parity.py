@@ -326,6 +326,25 @@ def test_sparse_index_mask_format(engine20, engine7, oracle20):
         assert ids.shape == (n, eng.max_legal) and (sparse.flags & 4).sum() == 0
         for i in range(n):
             assert ids[i, : cnt[i]].tolist() == np.flatnonzero(dense[i]).tolist()
+        # the sampler draws the same action whatever the mask format (index lists come straight from the fields)
+        a_idx = eng.step(s, None, mask="indices", sample=True, seed=4, env_id_base=77).next_action
+        a_byt = eng.step(s, None, mask="bytes", sample=True, seed=4, env_id_base=77).next_action
+        a_non = eng.step(s, None, mask=None, sample=True, seed=4, env_id_base=77).next_action
+        assert torch.equal(a_idx, a_byt) and torch.equal(a_idx, a_non) and bool((a_idx >= 0).all())
+    for (N, P) in ((14, 2), (9, 4)):                              # 14x14 specialisation and the runtime-dimension kernels
+        from blokus_rl_b200 import BlokusEngine
+        eng = BlokusEngine(N, P)
+        s = eng.new_states(200)
+        out = eng.step(s, None, mask="bytes", sample=True, seed=5)
+        for _ in range(10):
+            out = eng.step(s, out.next_action, mask="bytes", sample=True, seed=5)
+        sp = eng.step(s, None, mask="indices", sample=True, seed=5)
+        torch.cuda.synchronize()
+        ids, cnt, dense = sp.mask.cpu().numpy().view(np.uint16), sp.legal_count.cpu().numpy(), out.mask.cpu().numpy()
+        for i in range(200):
+            assert ids[i, : cnt[i]].tolist() == np.flatnonzero(dense[i]).tolist()
+        assert torch.equal(sp.next_action, out.next_action)
+        eng.close()
     # truncation is flagged, never silent: a 16-entry row cannot hold the 58 first moves
     s = engine20.new_states(2)
     small = torch.zeros((2, 16), dtype=torch.int16, device=s.device)

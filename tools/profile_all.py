@@ -103,11 +103,23 @@ def driver(only: set[str] | None, tag: str):
         eng.rollout(roots, 64, seed=7)
         capture("rollout", "rollout_kernel", 1024 * 1024, "playouts", lambda: eng.rollout(roots, 1024, seed=7),
                 "1,024 roots after 24 random plies x 1,024 playouts to terminal")
+    # the fused search: whole simulations in one kernel (one warp per tree; 8 warps on one tree with virtual loss)
+    for name, B, sims, wpt in (("search_b1", 1, 200, 1), ("search_b4096", 4096, 50, 1), ("search_b1_lp8", 1, 200, 8)):
+        if only and name not in only:
+            continue
+        roots, _ = midgame(eng, B, 23, None, seed=5)
+        search = GpuPuct(eng, num_trees=B, max_simulations=2 * sims + 8, mean_edges_per_node=420, warps_per_tree=wpt)
+        search.set_roots(roots)
+        search.run(sims)
+        search.set_roots(roots)
+        capture(name, "puct_search_kernel", B * sims, "simulations", lambda: search.run(sims),
+                f"{B} tree(s) x {sims} simulations in ONE launch, {wpt} warp(s) per tree, 24-ply 20x20 roots, uniform prior")
+        del search
     for name, B in (("puct", 16384), ("puct_b1", 1)):
         if only and name not in only:
             continue
         roots, _ = midgame(eng, B, 23, None, seed=5)
-        search = GpuPuct(eng, num_trees=B, max_simulations=64, mean_edges_per_node=420, use_cuda_graph=False)
+        search = GpuPuct(eng, num_trees=B, max_simulations=64, mean_edges_per_node=420, use_cuda_graph=False, fused=False)
         search.set_roots(roots)
         for _ in range(30):
             search.simulate()
@@ -181,7 +193,8 @@ def summarise(tag: str):
               "step_indices": "step_kernel_20_4_indices_65536", "step_unaligned": "step_kernel_20_4_unaligned_65536",
               "leaf_expand": "leaf_expand_20_4_65536", "observe": "observe_20_4_65536", "rollout": "rollout_kernel_20_4",
               "small7_bytes": "step_kernel_7_2_bytes_1048576", "small7_bits": "step_kernel_7_2_bits_1048576",
-              "small7_rollout": "rollout_kernel_7_2"}
+              "small7_rollout": "rollout_kernel_7_2", "search_b1": "search_kernel_20_4_b1", "search_b4096": "search_kernel_20_4_b4096",
+              "search_b1_lp8": "search_kernel_20_4_b1_lp8"}
     for t in meta["targets"]:
         pat = re.compile(t["kernel"])
         mine = []
