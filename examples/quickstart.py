@@ -4,7 +4,7 @@
 1. 4,096 envs of 20x20 four-player Blokus played with the on-device uniform-random policy (full legal masks every ply);
 2. the tensors a policy/value net consumes: obs float32 [B,8,20,20] + mask bool [B,30433];
 3. 100,000 random playouts from a mid-game position;
-4. a short PUCT search with the trees on the GPU.
+4. PUCT searches with the trees on the GPU: 256 at once, and ONE tree the way the reference's MCTS player searches.
 """
 import sys
 from pathlib import Path
@@ -34,10 +34,20 @@ ro = eng.rollout(roots, per_root=1000, seed=7)             # 100,000 playouts to
 print("playouts: mean final scores of root 0 =", ro.final_scores[0].float().mean(0).tolist(),
       "| value estimate =", (ro.value_sum[0] / 1000).tolist())
 
-search = GpuPuct(eng, num_trees=256, max_simulations=64)   # uniform prior (the reference's DumbNet); pass TorchNetEvaluator(net) for a real net
-search.set_roots(states[:256].contiguous())
-for _ in range(50):
-    search.simulate(cpuct=1.0)
+search = GpuPuct(eng, num_trees=256, max_simulations=64)   # uniform prior (the reference's DumbNet): whole simulations in one kernel;
+search.set_roots(states[:256].contiguous())                # pass TorchNetEvaluator(net) for a real net (lockstep kernels + the net)
+search.run(50, cpuct=1.0)                                  # 50 simulations of every tree: ONE launch
 print("PUCT: most visited root actions of the first 5 trees:", search.best_actions()[:5].tolist())
 meta, cells = eng.action_to_cells(int(search.best_actions()[0]))
 print("      tree 0 plays piece", meta[0], "covering cells", cells)
+
+# one tree, 200 simulations per move, tree kept across moves -- the reference's "mcts" arena player (players/mcts_player.py)
+from blokus_rl_b200.backend import EngineBackend
+from blokus_rl_b200.game_wrapper import BlokusGameWrapper
+from blokus_rl_b200.players import MCTSPlayer, RandomPlayer
+game = BlokusGameWrapper(board_size=20, number_of_players=4, backend=EngineBackend(engine=eng))
+players = [MCTSPlayer(game, simulations=200)] + [RandomPlayer(game) for _ in range(3)]     # reference_compat=False: 8 warps, virtual loss
+s, cur = game.get_init_board()
+while game.get_game_ended(s) is None:
+    s, cur = players[cur].update_state(s, cur)
+print("MCTS (seat 0) vs three random players, terminal vector:", game.get_game_ended(s).tolist())
