@@ -480,8 +480,9 @@ def run_ours(args):
         "counters": {"steps": int(ctr[0]), "games_finished_last_step": int(ctr[1]), "illegal": int(ctr[2])},
     }
     if prof:      # north_star: "integer-ALU/issue-slot utilisation" for the modes that are issue-bound, from the same capture
-        line["roofline_issue"] = {k: prof.get(k) for k in ("issue_slot_pct", "alu_pipe_pct", "warp_instr_per_unit",
-                                                           "warps_active_pct", "duration_us", "dram_pct") if k in prof}
+        line["roofline_issue"] = {k: prof.get(k) for k in ("issue_slot_pct", "alu_pipe_pct", "xu_pipe_pct", "smem_pipe_pct",
+                                                           "lsu_data_pipe_pct", "warp_instr_per_unit", "warps_active_pct",
+                                                           "duration_us", "dram_pct") if k in prof}
     if world == 1 and not args.no_extra and headline:
         line["extra"] = extra_workloads(eng, torch)
     if world == 1 and not args.no_cpu:
@@ -630,7 +631,10 @@ def run_search_workload(args, D: Dist, eng):
             ach = prof["warp_instr_per_unit"] * value / world / 1e12
             line["roofline"] = {"bound": "issue", "achieved": ach, "peak": peak, "unit": "T warp-instr/s", "frac": ach / peak,
                                 "traffic": prof.get("traffic"), "traffic_source": prof_note, "kernel": "rollout_kernel",
-                                "warp_instr_per_rollout": prof["warp_instr_per_unit"], "ncu_issue_slot_pct": prof.get("issue_slot_pct")}
+                                "warp_instr_per_rollout": prof["warp_instr_per_unit"], "ncu_issue_slot_pct": prof.get("issue_slot_pct"),
+                                # what actually binds it (ncu): the shared-memory pipe, with the ALU and XU pipes close behind
+                                "ncu_smem_pipe_pct": prof.get("smem_pipe_pct"), "ncu_alu_pipe_pct": prof.get("alu_pipe_pct"),
+                                "ncu_xu_pipe_pct": prof.get("xu_pipe_pct")}
         else:
             line["roofline"] = {"bound": "issue", "achieved": None, "peak": None, "unit": "T warp-instr/s", "frac": None,
                                 "traffic": None, "traffic_source": prof_note, "kernel": "rollout_kernel"}

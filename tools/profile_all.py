@@ -37,7 +37,13 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warp_latency_issue_stalled_barrier.pct', 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active']
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -226,6 +232,9 @@ def summarise(tag: str):
                    "issue_slot_pct": val('smsp__issue_active.avg.pct_of_peak_sustained_active'),
                    "alu_pipe_pct": val('sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active'),
                    "dram_pct": val('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'),
+                   "lsu_data_pipe_pct": val('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed'),
+                   "smem_pipe_pct": val('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed'),
+                   "xu_pipe_pct": val('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'),
                    "warps_active_pct": val('sm__warps_active.avg.pct_of_peak_sustained_active'),
                    "registers": val('launch__registers_per_thread'),
                    "warp_instr_per_unit": None if inst is None else inst / t["units"], "units": t["units"], "unit": t["unit"]}
