@@ -134,6 +134,18 @@ def driver(only: set[str] | None, tag: str):
         del search
     eng.close()
 
+    # the other warp-per-env instantiations: the 14x14 specialisation (Blokus Duo board) and the runtime-dimension kernels
+    for name, (N_, P_), E_ in (("step_14_2_bytes", (14, 2), 131072), ("step_runtime_10_2_bytes", (10, 2), 131072)):
+        if only and name not in only:
+            continue
+        eo = BlokusEngine(N_, P_)
+        st, buf = midgame(eo, E_, 10, "bytes", seed=9)
+        capture(name, "step_kernel", E_, "env steps",
+                lambda: eo.step(st, buf.next_action, buffers=buf, mask="bytes", sample=True, seed=9, auto_reset=True),
+                f"{N_}x{N_}/{P_}p, {E_} envs, byte masks, sampler on")
+        del st, buf
+        eo.close()
+
     e7 = BlokusEngine(7, 2)
     E7 = 1 << 20
     for name, fmt in (("small7_bytes", "bytes"), ("small7_bits", "bits")):
@@ -200,7 +212,8 @@ def summarise(tag: str):
               "leaf_expand": "leaf_expand_20_4_65536", "observe": "observe_20_4_65536", "rollout": "rollout_kernel_20_4",
               "small7_bytes": "step_kernel_7_2_bytes_1048576", "small7_bits": "step_kernel_7_2_bits_1048576",
               "small7_rollout": "rollout_kernel_7_2", "search_b1": "search_kernel_20_4_b1", "search_b4096": "search_kernel_20_4_b4096",
-              "search_b1_lp8": "search_kernel_20_4_b1_lp8"}
+              "search_b1_lp8": "search_kernel_20_4_b1_lp8", "step_14_2_bytes": "step_kernel_14_2_bytes_131072",
+              "step_runtime_10_2_bytes": "step_kernel_10_2_bytes_131072"}
     for t in meta["targets"]:
         pat = re.compile(t["kernel"])
         mine = []
