@@ -16,8 +16,8 @@
 //
 // warps_per_tree == 1 reproduces the reference's visit counts, Q values and per-simulation score vectors (tests:
 // golden vectors of the unmodified reference file).  warps_per_tree > 1 is leaf-parallel search with virtual loss: several
-// warps descend the same tree at once (claims by atomicCAS, backups under a per-tree lock) -- faster for ONE tree, not the
-// reference's visit order.
+// warps descend the same tree at once (claims by atomicCAS; an edge keeps the SUM of its backed-up values instead of their mean,
+// so a backup is atomic adds, no lock) -- faster for ONE tree, not the reference's visit order.
 #pragma once
 #include "blk_kernels.cuh"
 
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
     const blk_puct_forest &f = sp.f;
     unsigned char *tab = smem;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + sp.t.bytes);
-    int *blk_ctl = reinterpret_cast<int *>(smem + sp.t.bytes + 8);        // [0] tree lock, [1] simulations handed out
+    int *blk_ctl = reinterpret_cast<int *>(smem + sp.t.bytes + 8);        // [1] simulations handed out
     unsigned char *scratch = smem + sp.t.bytes + 16;
     if (kParallel && threadIdx.x == 0) { blk_ctl[0] = 0; blk_ctl[1] = 0; }
     tma_load_tables(tab, sp.tables, sp.t.bytes, bar);
@@ -328,10 +328,13 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
                 for (int k = 0; k < 4; ++k) {
                     const int i = i0 + 32 * k;
                     double nn = en[k], qq = eq[k];
-                    if (kParallel && vl[k] > 0) {           // pending visits count as visits that lost
+                    if (kParallel) {
+                        // leaf-parallel: edge_q holds the SUM of the backed-up values (so that a backup is two atomic adds, no
+                        // lock); pending visits (virtual loss) count as visits that lost `vloss`
                         const double v = static_cast<double>(vl[k]);
-                        qq = (nn * qq - v * vloss) / (nn + v);
-                        nn += v;
+                        const double den = nn + v;
+                        qq = den > 0.0 ? (qq - v * vloss) / den : 0.0;
+                        nn = den;
                     }
                     const double u = __ddiv_rn(cps, __dadd_rn(1.0, nn));
                     const double sc = __dadd_rn(qq, u);
@@ -436,28 +439,25 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
         // ---- backup: Q <- (N * Q + v) / (N + 1) with v = the score of the player to move AFTER the edge (mcts.py:53-56) ----
         if (lane < P) sscore[lane] = my_score;
         __syncwarp();
-        if (kParallel) {
-            if (lane == 0) while (atomicCAS(&blk_ctl[0], 0, 1) != 0) __nanosleep(40);
-            __syncwarp();
-            __threadfence();
-        }
         for (int d = lane; d < len; d += 32) {
             const int e = spath[d];
             const int child = d + 1 < len ? snode[d + 1] : last_child;   // the node the edge led to in THIS simulation
-            if (kParallel) atomicSub(f.edge_vl + e, 1);
             const double val = sscore[f.node_mover[child]];
-            const double nn = BLK_LD(f.edge_n + e), qq = BLK_LD(f.edge_q + e);
-            const double sn = BLK_LD(f.node_sum_n + snode[d]);
-            f.edge_q[e] = __ddiv_rn(__dadd_rn(__dmul_rn(nn, qq), val), __dadd_rn(nn, 1.0));
-            f.edge_n[e] = __dadd_rn(nn, 1.0);
-            f.node_sum_n[snode[d]] = __dadd_rn(sn, 1.0);                  // integer-valued: exact
+            if (kParallel) {
+                // several warps back up through the same edges: sums, not means, so that atomic adds suffice
+                atomicAdd(f.edge_q + e, val);
+                atomicAdd(f.edge_n + e, 1.0);
+                atomicAdd(f.node_sum_n + snode[d], 1.0);
+                atomicSub(f.edge_vl + e, 1);
+            } else {
+                const double nn = f.edge_n[e], qq = f.edge_q[e];
+                const double sn = f.node_sum_n[snode[d]];
+                f.edge_q[e] = __ddiv_rn(__dadd_rn(__dmul_rn(nn, qq), val), __dadd_rn(nn, 1.0));
+                f.edge_n[e] = __dadd_rn(nn, 1.0);
+                f.node_sum_n[snode[d]] = __dadd_rn(sn, 1.0);              // integer-valued: exact
+            }
         }
         __syncwarp();
-        if (kParallel) {
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) atomicExch(&blk_ctl[0], 0);
-        }
         if (lane < P) f.scores[static_cast<int64_t>(t) * P + lane] = my_score;
         __syncwarp();
     }

@@ -317,6 +317,8 @@ class GpuPuct:
         di = torch.as_tensor(idx, device=root.device, dtype=torch.long)
         cols = [self.t[k].index_select(0, di).cpu().numpy() for k in ("edge_action", "edge_n", "edge_q")]
         cols.append(np.zeros(len(idx)) if self.uniform else self.t["edge_p"].index_select(0, di).cpu().numpy())
+        if self.fused and self.warps_per_tree > 1:      # leaf-parallel search keeps SUMS of backed-up values per edge
+            cols[2] = np.where(cols[1] > 0, cols[2] / np.maximum(cols[1], 1.0), 0.0)
         parts = [np.split(c, np.cumsum(n)[:-1]) for c in cols]
         # nodes expanded with the uniform prior do not store P per edge: it is 1/nedge (the same float64 division)
         uni = self.t["node_uniform"].index_select(0, root).cpu().numpy()

@@ -50,7 +50,7 @@ class MCTSPlayer(Player):
     player, compare_arena.py:87-95; or :class:`RolloutEvaluator`) the ONE tree lives on the GPU and a whole move's search
     is a single launch of the fused search kernel (``blk_puct_search``): ``warps_per_tree = 1`` plays exactly the
     reference's search (same visit counts), ``warps_per_tree > 1`` is the faster leaf-parallel search with virtual loss
-    (``reference_compat=False`` selects 8 warps).  Network evaluators use the host-side :class:`BatchedMCTS`."""
+    (``reference_compat=False`` selects 16 warps).  Network evaluators use the host-side :class:`BatchedMCTS`."""
 
     def __init__(self, game, evaluator=None, simulations: int = 10, cpuct: float = 1.0, reference_compat: bool = True,
                  warps_per_tree: int | None = None, max_moves: int = 4 * 21 + 2):
@@ -62,7 +62,7 @@ class MCTSPlayer(Player):
         self.gpu = None
         if on_gpu and fusable:
             from .gpu_puct import GpuPuct
-            wpt = warps_per_tree if warps_per_tree is not None else (1 if reference_compat else 8)
+            wpt = warps_per_tree if warps_per_tree is not None else (1 if reference_compat else 16)
             self.gpu = GpuPuct(eng, self.evaluator, num_trees=1, max_simulations=(simulations + 1) * max_moves,
                                mean_edges_per_node=min(eng.num_actions, 600), warps_per_tree=wpt)
             self._fresh = True

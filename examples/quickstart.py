@@ -46,7 +46,7 @@ from blokus_rl_b200.backend import EngineBackend
 from blokus_rl_b200.game_wrapper import BlokusGameWrapper
 from blokus_rl_b200.players import MCTSPlayer, RandomPlayer
 game = BlokusGameWrapper(board_size=20, number_of_players=4, backend=EngineBackend(engine=eng))
-players = [MCTSPlayer(game, simulations=200)] + [RandomPlayer(game) for _ in range(3)]     # reference_compat=False: 8 warps, virtual loss
+players = [MCTSPlayer(game, simulations=200)] + [RandomPlayer(game) for _ in range(3)]     # reference_compat=False: 16 warps, virtual loss
 s, cur = game.get_init_board()
 while game.get_game_ended(s) is None:
     s, cur = players[cur].update_state(s, cur)

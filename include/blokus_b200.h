@@ -244,7 +244,8 @@ typedef struct {
     int32_t warps_per_tree;       /* 1: simulations of a tree run one after the other, exactly as the reference's (visit
                                      counts, Q and per-simulation scores are reproduced).  > 1 (<= 16): that many warps
                                      search the same tree at once with virtual loss -- leaf-parallel, NOT the reference's
-                                     visit order; needs edge_vl */
+                                     visit order; needs edge_vl.  In this mode edge_q holds the SUM of the values backed up
+                                     through the edge (Q = edge_q / edge_n), so that a backup is atomic adds */
     int32_t playouts_per_leaf;    /* 0: leaf value = 0 (DumbNet); k > 0: mean 3/1/-1 vector of k uniform-random playouts */
     uint64_t seed;                /* playout RNG key (stream 2) */
     double virtual_loss;          /* value a pending visit is counted as for its edge (leaf-parallel); 0 -> 1.0 */

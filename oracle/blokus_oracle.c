@@ -581,8 +581,8 @@ void orc_play_many(const orc_ctx *c, orc_state *states, int64_t n, uint64_t seed
 /* Uniform-random playout from `root` to the end of the game with the engine's playout stream (stream 1, key
  * seed_hi ^ game_index): final scores, winners bitmask, plies played; optional action log (0xFFFF terminated, like the
  * engine's).  stop_player >= 0 stops as soon as it is that player's turn.  Returns plies played. */
-int orc_playout(const orc_ctx *c, const orc_state *root, uint64_t seed, uint32_t game_index, int stop_player,
-                orc_state *out, int16_t *final_scores, int32_t *winners, uint16_t *action_log, int log_stride) {
+int orc_playout_stream(const orc_ctx *c, const orc_state *root, uint64_t seed, uint32_t game_index, uint32_t stream, int stop_player,
+                       orc_state *out, int16_t *final_scores, int32_t *winners, uint16_t *action_log, int log_stride) {
     uint32_t fields[MAXFIELDS];
     orc_state s = *root;
     int nply = 0;
@@ -592,7 +592,7 @@ int orc_playout(const orc_ctx *c, const orc_state *root, uint64_t seed, uint32_t
         if (cnt == 0) s.done = 1;
         while (!s.done) {
             if ((int)s.mover == stop_player) break;
-            const int a = pick_from_fields(c, fields, draw_k(&s, seed, game_index, 1, cnt));
+            const int a = pick_from_fields(c, fields, draw_k(&s, seed, game_index, stream, cnt));
             if (action_log && nply < log_stride - 1) action_log[nply] = (uint16_t)a;
             const int p = s.mover;
             place(c, &s, p, a);
@@ -611,4 +611,9 @@ int orc_playout(const orc_ctx *c, const orc_state *root, uint64_t seed, uint32_t
     if (winners) *winners = orc_winners(c, &s);
     if (out) *out = s;
     return nply;
+}
+/* the playout kernel's stream (1); the fused search kernel's in-kernel playouts use stream 2 */
+int orc_playout(const orc_ctx *c, const orc_state *root, uint64_t seed, uint32_t game_index, int stop_player,
+                orc_state *out, int16_t *final_scores, int32_t *winners, uint16_t *action_log, int log_stride) {
+    return orc_playout_stream(c, root, seed, game_index, 1, stop_player, out, final_scores, winners, action_log, log_stride);
 }

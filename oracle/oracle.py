@@ -71,6 +71,7 @@ def _load() -> C.CDLL:
     lib.orc_play_many.restype = None
     lib.orc_play_many.argtypes = [vp, vp, i64, u64, u32, u32, i32, i32, vp, i64, vp, vp, vp, i32, vp, vp, vp]
     lib.orc_playout.argtypes = [vp, vp, u64, u32, i32, vp, vp, vp, vp, i32]
+    lib.orc_playout_stream.argtypes = [vp, vp, u64, u32, u32, i32, vp, vp, vp, vp, i32]
     _lib = lib
     return lib
 
@@ -273,13 +274,13 @@ class Oracle:
         return {"traj": traj, "cnt_sum": cnt_sum, "sel_plies": sel, "ids_sum": ids_sum[:, :nsel], "words_sum": words_sum[:, :nsel],
                 "steps": int(ctr[0]), "games": int(ctr[1]), "legal_sum": int(ctr[2]), "threads": threads}
 
-    def playout(self, root, seed: int, game_index: int, stop_player: int = -1, log: bool = False):
+    def playout(self, root, seed: int, game_index: int, stop_player: int = -1, log: bool = False, stream: int = 1):
         """One uniform-random playout with the engine's playout stream: (plies, final scores, winners bitmask,
         end state, action log or None)."""
         out = C.create_string_buffer(self.state_size)
         scores = np.zeros(4, np.int16)
         win = C.c_int32(0)
         alog = np.zeros(88, np.uint16) if log else None
-        n = self.lib.orc_playout(self.ctx, root, seed, game_index, stop_player, out, scores.ctypes.data, C.byref(win),
-                                 _p(alog), 88)
+        n = self.lib.orc_playout_stream(self.ctx, root, seed, game_index, stream, stop_player, out, scores.ctypes.data,
+                                        C.byref(win), _p(alog), 88)
         return int(n), scores[: self.P].copy(), int(win.value), out, alog

@@ -47,3 +47,20 @@ def test_gpu_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 1e7
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and d["counters"]["illegal"] == 0
     assert d["value"] > 1e8 and "workload" in d["config"] and "l2" in d["config"]
+
+
+def test_reference_arm_rollouts_line():
+    d = _run("--impl", "reference", "--workload", "rollouts", "--steps", "2", "--warmup", "3")
+    assert d["impl"] == "reference" and d["unit"] == "rollouts/s" and d["metric"].startswith("MCTS rollouts/s")
+    assert d["value"] > 10 and d["cpu_baseline"]["kind"] == "port" and "playouts" in d["cpu_baseline"]["sample"]
+
+
+@pytest.mark.gpu
+def test_gpu_arm_search_workload_lines():
+    r = _run("--workload", "rollouts", "--steps", "2", "--roots", "256", "--per-root", "256")
+    assert r["metric"].startswith("MCTS rollouts/s") and r["unit"] == "rollouts/s" and r["value"] > 1e6 and r["gpu_launches"] == 2
+    assert r["counters"]["playouts"] == 256 * 256 and r["e2e"]["h2d_bytes_per_step"] > 0 and r["roofline"]["bound"] == "issue"
+    p = _run("--workload", "puct", "--steps", "2", "--roots", "64", "--sims", "20")
+    assert p["unit"] == "simulations/s" and p["value"] > 1e4 and p["counters"]["overflow"] == 0 and p["e2e"]["d2h_bytes_per_step"] == 4 * 64
+    q = _run("--workload", "puct", "--steps", "2", "--roots", "1", "--sims", "50", "--warps-per-tree", "8")
+    assert q["value"] > 1e4 and "8 warp(s) per tree" in q["config"]["workload"]
