@@ -28,7 +28,7 @@ sys.path.insert(0, str(ROOT))
 UNIT = "steps/s"
 ALG_BYTES = {"bytes": 31154, "bits": 4529}     # SURVEY.md section 8d / DESIGN.md: algorithmic HBM bytes per env step
 E2E_MIN_STEPS = 200                             # the end-to-end window never shrinks below this, whatever --steps says
-IDX_STRIDE = 768                                # uint16 ids per env row in the sparse-mask end-to-end leg
+IDX_STRIDE = 1024                               # uint16 ids per env row in the sparse-mask end-to-end leg (no 20x20 position is known to have more legal moves)
 
 
 def alg_bytes(fmt: str, N: int, P: int, A: int) -> int:
