@@ -28,7 +28,7 @@ sys.path.insert(0, str(ROOT))
 UNIT = "steps/s"
 ALG_BYTES = {"bytes": 31154, "bits": 4529}     # SURVEY.md section 8d / DESIGN.md: algorithmic HBM bytes per env step
 E2E_MIN_STEPS = 200                             # the end-to-end window never shrinks below this, whatever --steps says
-IDX_STRIDE = 1024                               # uint16 ids per env row in the sparse-mask end-to-end leg (no 20x20 position is known to have more legal moves)
+IDX_STRIDE = 1024                               # compact id array of the sparse-mask end-to-end leg: room for IDX_STRIDE / 2 ids per env on average
 
 
 def alg_bytes(fmt: str, N: int, P: int, A: int) -> int:
@@ -339,28 +339,33 @@ def e2e_leg(D: Dist, eng, states, act, fmt, seed, base, steps: int, halves: int)
     busy while the host consumes results): while one part's results travel to the host and its next actions come back,
     the other part's step kernel runs.  Every step of every env still pays its H2D action copy, its D2H result copies
     and a host synchronisation before the next actions are issued.
-    fmt 'indices': the mask itself comes back to the host every step, as the sorted legal ids (uint16 [IDX_STRIDE] per
-    env + the count) -- the reference's PPO contract (envs.get_attr("ai_possible_indexes"), ppo/trainer.py:385)."""
+    fmt 'csr': the mask itself comes back to the host every step, as the sorted legal ids of every env in one compact
+    array (BLK_MASK_INDICES with csr_cursor: as many uint16 entries as there are legal moves, + offset and count per env)
+    -- the reference's PPO contract (envs.get_attr("ai_possible_indexes"), ppo/trainer.py:385).  The host reads the
+    total first, then copies exactly that many ids: two synchronisations per part and step."""
     torch = D.torch
     P, n = eng.num_players, states.shape[0]
     H = max(1, halves)
     nh = n // H
-    sparse = fmt == "indices"
+    sparse = fmt == "csr"
+    pin = lambda shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
     parts = []
     for k in range(H):
         st = states[k * nh:(k + 1) * nh]
         if sparse:
             b = eng.make_buffers(nh, None, sample=True)
-            b.mask_raw = torch.empty((nh, IDX_STRIDE), dtype=torch.int16, device=D.dev)
+            b.mask_raw = torch.empty(nh * IDX_STRIDE // 2, dtype=torch.int16, device=D.dev)
+            b.csr_cursor = torch.zeros(1, dtype=torch.int64, device=D.dev)
+            b.csr_offset = torch.empty(nh, dtype=torch.int64, device=D.dev)
         else:
             b = eng.make_buffers(nh, fmt, sample=True)
         b.next_action.copy_(act[k * nh:(k + 1) * nh])
-        pin = lambda shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
         part = {"states": st, "buf": b, "stream": torch.cuda.Stream(device=D.dev), "event": torch.cuda.Event(),
                 "h_act": pin(nh, torch.int32), "h_flags": pin(nh, torch.uint8), "h_term": pin((nh, P), torch.float32),
                 "base": base + k * nh}
         if sparse:
-            part["h_ids"], part["h_cnt"] = pin((nh, IDX_STRIDE), torch.int16), pin(nh, torch.int32)
+            part.update(h_ids=pin(b.mask_raw.numel(), torch.int16), h_cnt=pin(nh, torch.int32), h_off=pin(nh, torch.int64),
+                        h_tot=pin(1, torch.int64), ev_tot=torch.cuda.Event())
         part["h_act"].copy_(b.next_action)
         parts.append(part)
     D.sync_all()
@@ -368,32 +373,39 @@ def e2e_leg(D: Dist, eng, states, act, fmt, seed, base, steps: int, halves: int)
     e0.record()
     for hv in parts:
         hv["stream"].wait_event(e0)
+    ids_bytes = 0
     for _ in range(steps):
         for hv in parts:
             hv["event"].synchronize()                              # the host needs this part's results to act on them
             with torch.cuda.stream(hv["stream"]):
                 b = hv["buf"]
                 b.next_action.copy_(hv["h_act"], non_blocking=True)          # host policy's actions -> device
-                o = eng.step(hv["states"], b.next_action, buffers=b, mask=b.mask_raw if sparse else fmt, sample=True,
+                o = eng.step(hv["states"], b.next_action, buffers=b, mask=fmt, sample=True,
                              seed=seed, env_id_base=hv["base"], auto_reset=True)
                 hv["h_act"].copy_(o.next_action, non_blocking=True)          # sampled legal actions -> host
                 hv["h_flags"].copy_(o.flags, non_blocking=True)              # done / illegal flags -> host
                 hv["h_term"].copy_(o.terminal, non_blocking=True)            # terminal vectors (rewards) -> host
                 if sparse:
-                    hv["h_ids"].copy_(b.mask_raw, non_blocking=True)         # the legal ids themselves -> host
+                    hv["h_tot"].copy_(o.csr_cursor, non_blocking=True)       # how many ids there are this step ...
                     hv["h_cnt"].copy_(o.legal_count, non_blocking=True)
+                    hv["h_off"].copy_(o.csr_offset, non_blocking=True)
+                    hv["ev_tot"].record()
+                    hv["ev_tot"].synchronize()
+                    tot = min(int(hv["h_tot"][0]), b.mask_raw.numel())
+                    hv["h_ids"][:tot].copy_(b.mask_raw[:tot], non_blocking=True)   # ... and exactly those ids -> host
+                    ids_bytes += 2 * tot
                 hv["event"].record()
     for hv in parts:
         torch.cuda.current_stream().wait_stream(hv["stream"])
     e1.record()
     D.sync_all()
     ms, per_rank = D.max_ms(e0.elapsed_time(e1))
-    d2h = (4 + 1 + 4 * P) + ((2 * IDX_STRIDE + 4) if sparse else 0)
+    d2h = (4 + 1 + 4 * P) * n + ((8 + 4 + 8) * n + ids_bytes // max(1, steps) if sparse else 0)
     truncated = int(sum(int((hv["h_flags"] & 4).sum()) for hv in parts)) if sparse else 0
     return {"value": D.world * nh * H * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * n * D.world,
-            "d2h_bytes_per_step": d2h * n * D.world, "steps": steps, "ms": ms,
+            "d2h_bytes_per_step": d2h * D.world, "steps": steps, "ms": ms,
             "per_rank_ms": [round(x, 3) for x in per_rank], "straggler_rank": int(max(range(len(per_rank)), key=per_rank.__getitem__)),
-            **({"ids_per_env_row": IDX_STRIDE, "truncated_rows_last_step": truncated} if sparse else {})}
+            **({"ids_bytes_per_env_step": round(ids_bytes / max(1, steps) / n, 1), "truncated_rows_last_step": truncated} if sparse else {})}
 
 
 def run_ours(args):
@@ -435,7 +447,7 @@ def run_ours(args):
 
     e2e_steps = max(E2E_MIN_STEPS, min(args.steps, 2000))
     e2e = e2e_leg(D, eng, states, act, fmt, seed, base, e2e_steps, args.e2e_halves)
-    e2e_sparse = e2e_leg(D, eng, states, act, "indices", seed, base, max(40, e2e_steps // 5), args.e2e_halves)
+    e2e_sparse = e2e_leg(D, eng, states, act, "csr", seed, base, max(40, e2e_steps // 5), args.e2e_halves)
     clocks = sampler.stop() if sampler else None
 
     # final counter reduction (the only collective): steps, finished games, illegal flags
@@ -469,8 +481,9 @@ def run_ours(args):
                          + (" (mask writes evict it every step)" if AB * n > 2 * 126e6 else " (not larger than L2: states stay L2-resident; see DESIGN.md)")},
         "e2e": {**{k: v for k, v in e2e.items() if k != "ms"}, "note": e2e_note},
         "e2e_mask_to_host": {**{k: v for k, v in e2e_sparse.items() if k != "ms"},
-                             "note": "the same loop with the legal mask itself returned to the host every step, as sorted legal ids "
-                                     "(BLK_MASK_INDICES, the reference's ai_possible_indexes contract, ppo/trainer.py:385)"},
+                             "note": "the same loop with the legal mask itself returned to the host every step, as the sorted legal ids of "
+                                     "every env in one compact array (BLK_MASK_INDICES + csr_cursor: the reference's ai_possible_indexes "
+                                     "contract, ppo/trainer.py:385); the host reads the total, then copies exactly that many ids"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": prof.get("traffic") if prof else None, "traffic_source": prof_note,

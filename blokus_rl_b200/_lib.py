@@ -44,7 +44,7 @@ class BlkStepArgs(C.Structure):
         ("mask", C.c_void_p), ("mask_format", C.c_int32), ("mask_stride", C.c_int64),
         ("legal_count", C.c_void_p), ("terminal", C.c_void_p), ("flags", C.c_void_p), ("scores", C.c_void_p),
         ("next_action", C.c_void_p), ("seed", C.c_uint64), ("env_id_base", C.c_uint32), ("options", C.c_uint32),
-        ("obs", C.c_void_p), ("state_index", C.c_void_p),
+        ("obs", C.c_void_p), ("state_index", C.c_void_p), ("csr_cursor", C.c_void_p), ("csr_offset", C.c_void_p),
     ]
 
 

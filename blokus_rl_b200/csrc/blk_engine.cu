@@ -561,6 +561,9 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
             return fail(BLK_ERR_ARG, "unknown mask_format");
         if (args->mask_format == BLK_MASK_INDICES && (!args->legal_count || args->mask_stride < 1))
             return fail(BLK_ERR_ARG, "BLK_MASK_INDICES needs legal_count and a positive mask_stride");
+        if ((args->csr_cursor != nullptr) != (args->csr_offset != nullptr) ||
+            (args->csr_cursor != nullptr && args->mask_format != BLK_MASK_INDICES))
+            return fail(BLK_ERR_ARG, "csr_cursor and csr_offset go together and belong to BLK_MASK_INDICES");
     }
     if (args->obs && (reinterpret_cast<uintptr_t>(args->obs) & 15) != 0) return fail(BLK_ERR_ARG, "obs must be 16 B aligned");
     if (args->state_index && (!args->state_out || args->state_out == args->state_in))
@@ -577,7 +580,7 @@ int blk_step(blk_engine *h, const blk_step_args *args, void *stream) {
         variant = 3;
     const bool bits_rows_8b = variant != BLK_MASK_BITS ||
                               ((args->mask_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(args->mask) & 7) == 0);
-    if (h->small && bits_rows_8b && !(args->options & BLK_OPT_WARP_KERNELS)) {
+    if (h->small && bits_rows_8b && !(args->options & BLK_OPT_WARP_KERNELS) && args->csr_cursor == nullptr) {   // (compact index lists: warp kernels)
         // N <= 7: one env per thread on 64-bit bitboards (blk_small.cu); the other formats stay on the warp-per-env kernel
         SmallParams sp;
         sp.a = *args; sp.tables = h->d_tables; sp.t = h->t; sp.g = h->g;

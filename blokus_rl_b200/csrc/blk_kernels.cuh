@@ -746,6 +746,18 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
             const int incl = warp_incl_scan(mine, lane);
             cnt = __shfl_sync(kAllLanes, incl, 31);
             uint16_t *irow = reinterpret_cast<uint16_t *>(a.mask) + env * mstride;
+            int64_t room = mstride;
+            if (a.csr_cursor != nullptr) {
+                // compact form: this env's ids go behind whatever the envs before it (in launch order) asked for
+                unsigned long long base = 0ULL;
+                if (lane == 0) {
+                    base = atomicAdd(a.csr_cursor, static_cast<unsigned long long>(cnt));
+                    a.csr_offset[env] = static_cast<int64_t>(base);
+                }
+                base = __shfl_sync(kAllLanes, base, 0);
+                irow = reinterpret_cast<uint16_t *>(a.mask) + base;
+                room = static_cast<int64_t>(base) + cnt <= mstride ? cnt : 0;      // all of the env's ids or none
+            }
             int pos = incl - mine;
             const int chunk = kN == 20 ? 52 : per;
             const int i0 = lane * chunk;
@@ -757,7 +769,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                     if (w) {
                         const int base = tb.foff[i];
                         do {
-                            if (pos < mstride) irow[pos] = static_cast<uint16_t>(base + __ffs(w) - 1);
+                            if (pos < room) irow[pos] = static_cast<uint16_t>(base + __ffs(w) - 1);
                             ++pos;
                             w &= w - 1;
                         } while (w);
@@ -765,7 +777,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                 }
             }
             __syncwarp();
-            if (cnt > mstride) flags |= BLK_FLAG_TRUNCATED;
+            if (cnt > room) flags |= BLK_FLAG_TRUNCATED;
             if (kSample && cnt > 0) {
                 const uint32_t ply = e.meta >> 16;
                 const uint32_t u = philox_word(philox4(ply >> 2, e.game, 0u, 0u, static_cast<uint32_t>(a.seed),

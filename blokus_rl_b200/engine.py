@@ -30,6 +30,8 @@ class StepOut:
     next_action: torch.Tensor | None     # int32 [n]        uniform random legal action of the new mover
     mask_raw: torch.Tensor | None = None # the padded buffer behind `mask`
     obs: torch.Tensor | None = None      # float32 [n, 2P, N, N] observation of the resulting states (fused output)
+    csr_offset: torch.Tensor | None = None   # mask="csr": int64 [n], env i's ids are mask_raw[csr_offset[i] : + legal_count[i]]
+    csr_cursor: torch.Tensor | None = None   # mask="csr": int64 [1], total entries requested by this call
 
 
 @dataclass
@@ -162,6 +164,22 @@ class BlokusEngine:
             raise ValueError("out_states must have one row per env")
         b = buffers
         raw_mask, fmt, stride = None, BLK_MASK_NONE, 0
+        csr_cursor = csr_offset = None
+        if isinstance(mask, str) and mask == "csr":
+            # compact index lists: one flat uint16 array for the whole batch (blk_step_args.csr_cursor / csr_offset)
+            raw_mask = getattr(b, "mask_raw", None) if b is not None else None
+            if raw_mask is None:
+                raw_mask = torch.empty(n * min(self.max_legal, 512), dtype=torch.int16, device=dev)
+            if raw_mask.dtype != torch.int16 or raw_mask.dim() != 1 or not raw_mask.is_contiguous() or raw_mask.device != dev:
+                raise ValueError("mask='csr' needs a flat contiguous int16 CUDA buffer in buffers.mask_raw")
+            csr_cursor = getattr(b, "csr_cursor", None) if b is not None else None
+            csr_cursor = torch.zeros(1, dtype=torch.int64, device=dev) if csr_cursor is None else csr_cursor.zero_()
+            csr_offset = getattr(b, "csr_offset", None) if b is not None else None
+            if csr_offset is None:
+                csr_offset = torch.empty(n, dtype=torch.int64, device=dev)
+            if csr_offset.dtype != torch.int64 or csr_offset.shape[0] < n or csr_offset.device != dev:
+                raise ValueError("buffers.csr_offset must be an int64 [n] CUDA tensor")
+            fmt, stride, want_count, mask = BLK_MASK_INDICES, raw_mask.numel(), True, None
         if isinstance(mask, torch.Tensor):
             raw_mask = mask
         elif mask is not None:
@@ -173,7 +191,7 @@ class BlokusEngine:
                 raise ValueError(f"buffers hold a {raw_mask.dtype} mask but mask={mask!r} was requested")
             if raw_mask is None:
                 raw_mask = self.alloc_mask(n, mask)
-        if raw_mask is not None:
+        if raw_mask is not None and csr_cursor is None:
             if raw_mask.dtype == torch.int32:
                 fmt, stride = BLK_MASK_BITS, raw_mask.stride(0)
             elif raw_mask.dtype in (torch.uint8, torch.bool):
@@ -224,9 +242,12 @@ class BlokusEngine:
             None if scores is None else scores.data_ptr(),
             None if next_action is None else next_action.data_ptr(),
             seed & 0xFFFFFFFFFFFFFFFF, env_id_base & 0xFFFFFFFF, (BLK_OPT_AUTO_RESET if auto_reset else 0) | (BLK_OPT_WARP_KERNELS if warp_kernels else 0),
-            None if obs is None else obs.data_ptr(), None if state_index is None else state_index.data_ptr())
+            None if obs is None else obs.data_ptr(), None if state_index is None else state_index.data_ptr(),
+            None if csr_cursor is None else csr_cursor.data_ptr(), None if csr_offset is None else csr_offset.data_ptr())
         _lib.check(self._lib.blk_step(self._h, C.byref(args), self._stream()))
         view = None
+        if csr_cursor is not None:
+            return StepOut(out_states, raw_mask, legal_count, terminal, flags, scores, next_action, raw_mask, obs, csr_offset, csr_cursor)
         if raw_mask is not None:
             view = self.mask_view(raw_mask) if fmt == BLK_MASK_BYTES and raw_mask.shape[1] >= self.num_actions and \
                 raw_mask.dtype == torch.uint8 else raw_mask

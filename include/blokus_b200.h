@@ -39,7 +39,7 @@ extern "C" {
  * (step states out of a pool), blk_rollout_args grew `options`, BLK_OPT_WARP_KERNELS, blk_puct_forest grew `node_uniform`
  * and a 6th counter, blk_puct_expand_args grew `fuse_backup`.  All additions are trailing fields: zero-initialised structs keep
  * their version-1 meaning.
- * 3 = blk_puct_forest grew the board-keyed node table (hash_table, hash_capacity, node_hash, node_tree), edge_vl and node_front;
+ * 3 = blk_step_args grew csr_cursor / csr_offset (compact index lists); blk_puct_forest grew the board-keyed node table (hash_table, hash_capacity, node_hash, node_tree), edge_vl and node_front;
  * blk_puct_search / blk_puct_reroot (whole simulations inside one kernel); work-queue slots are per stream / per graph capture;
  * every entry point restores the caller's current device. */
 #define BLK_ABI_VERSION 3
@@ -110,6 +110,13 @@ typedef struct {
                                    policy/value net is then one launch: new state + legal mask + observation */
     const int32_t *state_index; /* nullable [n]: env i reads state_in[state_index[i]] instead of state_in[i] (a search tree
                                    stepping states out of its node pool: no gather pass; state_out must not alias state_in) */
+    /* BLK_MASK_INDICES, compact form (both NULL = padded rows).  With csr_cursor set, `mask` is ONE flat uint16 array of
+     * mask_stride entries shared by all envs: env i's ids occupy [csr_offset[i], csr_offset[i] + legal_count[i]) -- as
+     * many bytes as there are legal moves (~350 B per env at 20x20 instead of a 2 KB row), which is what a host-side policy
+     * wants to copy back.  The caller zeroes *csr_cursor before the call; afterwards it holds the entries requested (envs land
+     * in launch order, not env order).  An env whose ids do not fit any more is flagged BLK_FLAG_TRUNCATED and writes none. */
+    unsigned long long *csr_cursor;   /* nullable device counter */
+    int64_t *csr_offset;              /* [n], required with csr_cursor */
 } blk_step_args;
 
 /* Arguments of blk_rollout(): uniform-random playouts to the end of the game, one warp per game. */

@@ -35,7 +35,7 @@ def test_abi_version_and_struct_sizes(lib):
     from blokus_rl_b200 import _lib
     assert lib.blk_abi_version() == 3
     assert C.sizeof(_lib.BlkConfig) == 16 and C.sizeof(_lib.BlkInfo) == 44
-    assert C.sizeof(_lib.BlkStepArgs) == 128 and C.sizeof(_lib.BlkRolloutArgs) == 112
+    assert C.sizeof(_lib.BlkStepArgs) == 144 and C.sizeof(_lib.BlkRolloutArgs) == 112
 
 
 def test_ctypes_structs_have_the_c_layout(tmp_path):
@@ -43,7 +43,7 @@ def test_ctypes_structs_have_the_c_layout(tmp_path):
     import subprocess
     from blokus_rl_b200 import _lib
     pairs = [("blk_config", _lib.BlkConfig, "device"), ("blk_info", _lib.BlkInfo, "sm_count"),
-             ("blk_step_args", _lib.BlkStepArgs, "state_index"), ("blk_rollout_args", _lib.BlkRolloutArgs, "options"),
+             ("blk_step_args", _lib.BlkStepArgs, "csr_offset"), ("blk_rollout_args", _lib.BlkRolloutArgs, "options"),
              ("blk_puct_forest", _lib.BlkPuctForest, "node_front"), ("blk_puct_expand_args", _lib.BlkPuctExpandArgs, "fuse_backup"),
              ("blk_puct_search_args", _lib.BlkPuctSearchArgs, "virtual_loss")]
     body = "".join(f'printf("%zu %zu\\n", sizeof({c}), offsetof({c}, {last}));' for c, _, last in pairs)

@@ -345,6 +345,36 @@ def test_sparse_index_mask_format(engine20, engine7, oracle20):
             assert ids[i, : cnt[i]].tolist() == np.flatnonzero(dense[i]).tolist()
         assert torch.equal(sp.next_action, out.next_action)
         eng.close()
+    # compact form (blk_step_args.csr_cursor / csr_offset): one flat array, as many entries as there are legal moves
+    for eng in (engine20, engine7):
+        n = 777
+        s = eng.new_states(n)
+        out = eng.step(s, None, mask="bytes", sample=True, seed=6)
+        for _ in range(14 if eng.board_size == 20 else 3):
+            out = eng.step(s, out.next_action, mask="bytes", sample=True, seed=6)
+        c = eng.step(s, None, mask="csr", sample=True, seed=6)
+        torch.cuda.synchronize()
+        flat, off, cnt = c.mask_raw.cpu().numpy().view(np.uint16), c.csr_offset.cpu().numpy(), c.legal_count.cpu().numpy()
+        dense = out.mask.cpu().numpy()
+        assert int(c.csr_cursor.item()) == int(cnt.sum()) == int(dense.sum()) and not (c.flags.cpu().numpy() & 4).any()
+        spans = sorted((int(o), int(k)) for o, k in zip(off, cnt))
+        assert spans[0][0] == 0 and all(a + k == b for (a, k), (b, _) in zip(spans, spans[1:]))      # the envs tile the array
+        for i in range(n):
+            assert flat[off[i]: off[i] + cnt[i]].tolist() == np.flatnonzero(dense[i]).tolist()
+        assert torch.equal(c.next_action, out.next_action)
+        # too small an array: envs that do not fit are flagged and write nothing; the others are complete
+        from blokus_rl_b200.engine import StepOut
+        cap = int(cnt.sum()) // 2
+        small = StepOut(None, None, None, None, None, None, None, torch.full((cap,), -1, dtype=torch.int16, device=s.device))
+        c2 = eng.step(s, None, mask="csr", buffers=small)
+        torch.cuda.synchronize()
+        fl, off2, flat2 = c2.flags.cpu().numpy(), c2.csr_offset.cpu().numpy(), c2.mask_raw.cpu().numpy().view(np.uint16)
+        assert (fl & 4).any() and not (fl & 4).all() and int(c2.csr_cursor.item()) == int(cnt.sum())
+        for i in range(n):
+            if fl[i] & 4:
+                assert off2[i] + cnt[i] > cap
+            else:
+                assert flat2[off2[i]: off2[i] + cnt[i]].tolist() == np.flatnonzero(dense[i]).tolist()
     # truncation is flagged, never silent: a 16-entry row cannot hold the 58 first moves
     s = engine20.new_states(2)
     small = torch.zeros((2, 16), dtype=torch.int16, device=s.device)
