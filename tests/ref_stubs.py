@@ -43,6 +43,8 @@ def install_stubs():
     gym.spaces = mod("gymnasium.spaces", Discrete=object, Box=object)
     plt = mod("matplotlib.pyplot")
     mod("tensorboard")
+    mod("torch.utils.tensorboard", SummaryWriter=lambda *a, **k: types.SimpleNamespace(add_scalar=lambda *a, **k: None, add_text=lambda *a, **k: None,
+                                                                                         add_graph=lambda *a, **k: None, close=lambda: None))
     mod("matplotlib", pyplot=plt)
     mod("torchsummary", summary=lambda *a, **k: None)
     mod("pytablewriter", MarkdownTableWriter=object)

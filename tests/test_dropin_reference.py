@@ -124,3 +124,69 @@ def test_reference_wrapper_over_shim_at_7x7_two_players(tmp_path):
     finally:
         os.chdir(cwd)
         colosseum_shim.set_backend(None)
+
+
+def _reference_self_play_episode(backend, work, N, P, sims, seed):
+    """AlphaZeroTrainer._self_play (blokus_rl/alphazero/trainer.py:92-137), the reference's own method, run unmodified on a
+    stand-in `self` that carries what it reads: game, nnet, hparams.num_mcts_sims / cpuct."""
+    from blokus_rl_b200 import colosseum_shim
+    colosseum_shim.set_backend(backend)
+    colosseum_shim.install()
+    ref_stubs.install_stubs()
+    from blokus_rl.alphazero.trainer import AlphaZeroTrainer
+    from blokus_rl.colossumrl.blokus_wrapper import ColosseumBlokusGameWrapper
+    game = ColosseumBlokusGameWrapper(types.SimpleNamespace(board_size=N, number_of_players=P, states_dir=work / "states"))
+    me = types.SimpleNamespace(game=game, nnet=UniformNet(P), hparams=types.SimpleNamespace(num_mcts_sims=sims, cpuct=1.0))
+    np.random.seed(seed)
+    return AlphaZeroTrainer._self_play(me, 1)
+
+
+def test_reference_self_play_episode_over_shim(tmp_path):
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        from blokus_rl_b200 import colosseum_shim
+        data = _reference_self_play_episode(OracleBackend(7, 2), tmp_path, 7, 2, sims=5, seed=0)
+    finally:
+        os.chdir(cwd)
+        colosseum_shim.set_backend(None)
+    assert 4 <= len(data) <= 42
+    for obs, mask, prob, scores in data:                              # trainer.py:118-121, what AlphaZeroDataset reads
+        assert obs.shape == (4, 7, 7) and mask.shape == (2522,) and mask.dtype == np.float64
+        assert prob.dtype == np.float32 and len(prob) == int(mask.sum()) and abs(float(prob.sum()) - 1) < 1e-5
+        assert set(np.unique(scores)) <= {-1.0, 1.0, 3.0}
+
+
+def _reference_ppo_rollouts(engine, tmp, num_envs=4, num_steps=24, seed=7):
+    """PPOTrainer._play_env + _compute_gae (blokus_rl/ppo/trainer.py:128-175, 177-205), the reference's own methods with its own
+    CnnAgent, FilterLegalMoves and Memory, run unmodified over BlokusVectorEnv (boundary B2) on a stand-in `self`."""
+    import torch
+    from blokus_rl_b200.vector_env import BlokusVectorEnv
+    ref_stubs.install_stubs()
+    from blokus_rl.hparams import PPOHparams
+    from blokus_rl.ppo.agent import get_agent
+    from blokus_rl.ppo.memory import Memory
+    from blokus_rl.ppo.trainer import PPOTrainer
+    hp = PPOHparams(num_envs=num_envs, num_steps=num_steps, agent_type="cnn", cuda=False, seed=seed)
+    envs = BlokusVectorEnv(hp.num_envs, engine=engine, seed=hp.seed)
+    torch.manual_seed(seed)
+    agent = get_agent(hp.agent_type)(envs, hp).eval()
+    me = types.SimpleNamespace(hparams=hp, device="cpu", envs=envs, agent=agent, memory=Memory(hp, envs, "cpu"), global_step=0,
+                               _total_episodes=0, _total_episodes_reward=0)
+    me.running_vals = PPOTrainer._reset_running_vals(me)
+    for name in ("_get_valid_moves_mask", "_update_running_vals", "_compute_gae"):
+        setattr(me, name, types.MethodType(getattr(PPOTrainer, name), me))
+    obs, _ = envs.reset()
+    next_obs, next_done = PPOTrainer._play_env(me, torch.Tensor(obs), torch.zeros(hp.num_envs))
+    with torch.inference_mode():
+        adv = me._compute_gae(agent.get_value(next_obs).reshape(1, -1), next_done)
+    return me, adv
+
+
+def test_reference_ppo_rollout_collection_over_vector_env(tmp_path):
+    from oracle_engine import OracleEngine
+    me, adv = _reference_ppo_rollouts(OracleEngine(7, 2), tmp_path)
+    m = me.memory
+    assert me.global_step == 4 * 24 and me._total_episodes >= 2 and adv.shape == (24, 4)
+    assert m.obs.shape == (24, 4, 7, 7) and set(np.unique(m.rewards.numpy())) <= {-1.0, 0.0, 1.0}
+    assert (m.actions >= 0).all() and (m.actions < 2522).all() and m.dones.sum() >= 2

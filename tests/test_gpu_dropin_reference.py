@@ -145,3 +145,30 @@ def test_gpu_mcts_player_plays_the_reference_mcts_players_moves(chdir_tmp):
         cur = nxt
         plies += 1
     assert plies >= 6 and ours.get_game_ended(s_our) is not None
+
+
+def test_reference_self_play_episode_on_the_gpu_equals_the_one_on_the_oracle(chdir_tmp):
+    """AlphaZeroTrainer._self_play (alphazero/trainer.py:92-137), the reference's own method, unmodified: the same seeded
+    episode over the CUDA engine and over the CPU oracle backend produces the same training examples, one by one."""
+    from test_dropin_reference import _reference_self_play_episode
+    from blokus_rl_b200.backend import EngineBackend
+    from oracle_backend import OracleBackend
+    on_gpu = _reference_self_play_episode(EngineBackend(7, 2), chdir_tmp, 7, 2, sims=6, seed=3)
+    on_cpu = _reference_self_play_episode(OracleBackend(7, 2), chdir_tmp, 7, 2, sims=6, seed=3)
+    assert len(on_gpu) == len(on_cpu) >= 4
+    for (og, mg, pg, sg), (oc, mc, pc, sc) in zip(on_gpu, on_cpu):
+        assert (og == oc).all() and (mg == mc).all() and (pg == pc).all() and (sg == sc).all()
+
+
+def test_reference_ppo_rollout_collection_on_the_gpu_env(engine7, tmp_path):
+    """ppo/trainer.py:128-175 (the reference's `_play_env`, unmodified, with its own CnnAgent / FilterLegalMoves / Memory):
+    the rollout buffer it fills over BlokusVectorEnv on the CUDA engine (opponents, autoreset and legal ids on the device) is the
+    buffer it fills over the CPU stand-in engine, step by step."""
+    import torch
+    from oracle_engine import OracleEngine
+    from test_dropin_reference import _reference_ppo_rollouts
+    gpu, adv_g = _reference_ppo_rollouts(engine7, tmp_path)
+    cpu, adv_c = _reference_ppo_rollouts(OracleEngine(7, 2), tmp_path)
+    for name in ("obs", "actions", "rewards", "dones", "logprobs", "values"):
+        assert torch.equal(getattr(gpu.memory, name), getattr(cpu.memory, name)), name
+    assert torch.equal(adv_g, adv_c) and gpu._total_episodes == cpu._total_episodes >= 2
