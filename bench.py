@@ -114,7 +114,7 @@ class CpuArm:
         return n * per_root, sum(plies), time.perf_counter() - t0
 
 
-def reference_wrapper_rate(N: int, P: int, seconds: float = 3.0):
+def reference_wrapper_rate(N: int, P: int, seconds: float = 3.0, backend=None, ours: bool = False):
     """the REFERENCE's own wrapper code path (blokus_rl/colossumrl/blokus_wrapper.py:233-246, 89-132,
     164-186: get_sample_move -> get_next_state -> get_valid_moves -> get_game_ended), unmodified, one process = how the
     reference runs, with the CPU oracle as the engine under the colosseumrl shim.  None when the reference's Python package
@@ -126,9 +126,11 @@ def reference_wrapper_rate(N: int, P: int, seconds: float = 3.0):
             return None
         import tempfile
         import types
-        from oracle_backend import OracleBackend
         from blokus_rl_b200 import colosseum_shim
-        colosseum_shim.set_backend(OracleBackend(N, P))
+        if backend is None:
+            from oracle_backend import OracleBackend
+            backend = OracleBackend(N, P)
+        colosseum_shim.set_backend(backend)
         colosseum_shim.install()
         ref_stubs.install_stubs()
         cwd, work = os.getcwd(), Path(tempfile.mkdtemp())
@@ -136,8 +138,12 @@ def reference_wrapper_rate(N: int, P: int, seconds: float = 3.0):
         try:
             import logging
             logging.disable(logging.WARNING)
-            from blokus_rl.colossumrl.blokus_wrapper import ColosseumBlokusGameWrapper
-            game = ColosseumBlokusGameWrapper(types.SimpleNamespace(board_size=N, number_of_players=P, states_dir=work / "states"))
+            if ours:                                     # boundary B1: this repo's sibling of the wrapper (ids, no string round trip)
+                from blokus_rl_b200.game_wrapper import BlokusGameWrapper
+                game = BlokusGameWrapper(board_size=N, number_of_players=P, backend=backend)
+            else:
+                from blokus_rl.colossumrl.blokus_wrapper import ColosseumBlokusGameWrapper
+                game = ColosseumBlokusGameWrapper(types.SimpleNamespace(board_size=N, number_of_players=P, states_dir=work / "states"))
             plies, t0 = 0, time.perf_counter()
             while time.perf_counter() - t0 < seconds:
                 s, p = game.get_init_board()
@@ -777,6 +783,16 @@ def extra_workloads(eng, torch):
             agent_step()
         extra[f"ppo_numpy_surface_agent_steps_per_s_{E}_envs"] = E * reps / (time.perf_counter() - t0)
     e7.close()
+    # boundaries B0 / B1 on the GPU, one state at a time (how the reference's own loops call the env): the reference's unmodified
+    # wrapper over the colosseumrl shim over the CUDA engine, and this repo's BlokusGameWrapper; one launch + one D2H per ply
+    from blokus_rl_b200.backend import EngineBackend
+    eb = EngineBackend(engine=eng)
+    w0 = reference_wrapper_rate(20, 4, 2.0, backend=eb)
+    if w0 is not None:
+        extra["b0_reference_wrapper_over_gpu_plies_per_s"] = w0.get("value", w0.get("error"))
+    w1 = reference_wrapper_rate(20, 4, 2.0, backend=eb, ours=True)
+    if w1 is not None:
+        extra["b1_game_wrapper_over_gpu_plies_per_s"] = w1.get("value", w1.get("error"))
     # device-resident PUCT forest (config/mcts_blokus.yml player: MCTS with the uniform DumbNet prior)
     from blokus_rl_b200.gpu_puct import GpuPuct
 
