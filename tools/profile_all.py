@@ -204,6 +204,16 @@ def summarise(tag: str):
                "tree_hash_at_summary": here, "gpu": meta.get("gpu"), "kernels": {}}
     if here != meta["source_hash"]:
         print(f"WARNING: the tree's kernel sources ({here}) are not the ones the capture ran on ({meta['source_hash']})")
+    # a capture may come in several parts (gpurun brings back at most 64 MiB per call): keep what another part of the SAME
+    # sources already put into traffic.json
+    old_tf = ROOT / "profiles" / "traffic.json"
+    if old_tf.exists():
+        try:
+            old = json.loads(old_tf.read_text())
+            if old.get("source_hash") == meta["source_hash"]:
+                traffic["kernels"].update(old.get("kernels", {}))
+        except ValueError:
+            pass
     import re
     pos = 0
     prof_dir = ROOT / "profiles"
