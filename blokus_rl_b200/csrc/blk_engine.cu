@@ -446,7 +446,7 @@ int blk_create(const blk_config *cfg, blk_engine **out) {
     else if (N == 14 && P == 2) { h->ks = kernels_14_2(); h->sk = search_kernels_14_2(); geom = 4; }
     else if (N == 7 && P == 2) { h->ks = kernels_7_2(); h->sk = search_kernels_7_2(); geom = 5; }
     else { h->ks = kernels_0_0(); h->sk = search_kernels_0_0(); }
-    h->search_smem_per_warp = h->g.warp_smem + 2 * kSearchMaxIds + 8 * kSearchMaxDepth + 64;
+    h->search_smem_per_warp = search_warp_bytes(h->g.warp_smem);
     h->special = geom != 0;
     // the attribute is per function, not per engine: only ever raise it (engines of several board sizes coexist)
     static int s_max_smem[16][6] = {};

@@ -26,6 +26,11 @@ namespace blk {
 constexpr int kSearchTrees = 4;        // trees per block when every tree has one warp
 constexpr int kSearchMaxIds = 1024;    // legal ids compacted per sweep (20x20 positions have <= ~800)
 constexpr int kSearchMaxDepth = 96;    // >= 4 * 21 placements + 1
+// per-warp shared memory: fields (+ scratch) | compacted ids | path: edge and node (int each) | the simulation's score vector.
+// At 20x20 that is 9,680 B per tree: 4 trees + the 19 KB of tables = 57.7 KB per block, FOUR blocks per SM.  (Carrying the
+// edges' N / Q and the nodes' sum N along the path in shared memory, so that the backup needs no global load, was measured:
+// +6 % for one tree, but 12.4 KB per tree leaves three blocks per SM and 4,096 trees ran 23 % slower.)
+__host__ __device__ constexpr int search_warp_bytes(int warp_smem) { return warp_smem + 2 * kSearchMaxIds + 8 * kSearchMaxDepth + 64; }
 
 struct SearchParams {
     blk_puct_forest f;
@@ -131,9 +136,10 @@ template <int kN, bool kFence>
 __device__ __forceinline__ bool expand_from_fields(const blk_puct_forest &f, int node, const uint32_t *fld, uint16_t *ids,
                                                    const SmemTables &tb, int nf, int lane) {
     const int per = (nf + 31) >> 5;
-    const int i0 = lane * per, i1 = min(i0 + per, nf);
-    int mine = 0;
-    for (int i = i0; i < i1; ++i) mine += __popc(fld[i]);
+    const int mine = count_field_chunk<kN>(fld, nf, per, lane);       // lane l owns fields [l * chunk, + len): 13 LDS.128 at N = 20
+    const int chunk = kN == 20 ? 52 : per;
+    const int i0 = lane * chunk;
+    const int len = kN == 20 ? (lane == 31 ? 53 : 52) : max(0, min(per, nf - i0));
     const int incl = warp_incl_scan(mine, lane);
     const int n = __shfl_sync(kAllLanes, incl, 31);
     int e0 = 0;
@@ -143,15 +149,36 @@ __device__ __forceinline__ bool expand_from_fields(const blk_puct_forest &f, int
     const int skip = incl - mine;                          // this lane's first position in id order
     for (int done_e = 0; done_e < n; done_e += kSearchMaxIds) {
         int pos = skip - done_e;
-        for (int i = i0; i < i1; ++i) {
-            uint32_t w = fld[i];
-            const int base = tb.foff[i];
-            while (w) {
-                if (pos >= 0 && pos < kSearchMaxIds) ids[pos] = static_cast<uint16_t>(base + __ffs(w) - 1);
-                ++pos;
-                w &= w - 1;
+        // ids of one field, appended at `pos` (window [0, kSearchMaxIds) of this sweep)
+#define BLK_EMIT_FIELD(w_, i_)                                                                        \
+        {                                                                                             \
+            uint32_t w = (w_);                                                                        \
+            if (w) {                                                                                  \
+                const int base = tb.foff[i_];                                                         \
+                do {                                                                                  \
+                    if (pos >= 0 && pos < kSearchMaxIds) ids[pos] = static_cast<uint16_t>(base + __ffs(w) - 1); \
+                    ++pos;                                                                            \
+                    w &= w - 1;                                                                       \
+                } while (w);                                                                          \
+            }                                                                                         \
+        }
+        if (mine > 0) {
+            if (kN == 20) {                                 // four fields per load; most quads of a mid-game position are empty
+                const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 13 * lane;
+#pragma unroll 1
+                for (int j = 0; j < 13; ++j) {
+                    const uint4 x = f4[j];
+                    if ((x.x | x.y | x.z | x.w) != 0u) {
+                        BLK_EMIT_FIELD(x.x, i0 + 4 * j) BLK_EMIT_FIELD(x.y, i0 + 4 * j + 1)
+                        BLK_EMIT_FIELD(x.z, i0 + 4 * j + 2) BLK_EMIT_FIELD(x.w, i0 + 4 * j + 3)
+                    }
+                }
+                if (lane == 31) BLK_EMIT_FIELD(fld[1664], 1664)
+            } else {
+                for (int t = 0; t < len; ++t) BLK_EMIT_FIELD(fld[i0 + t], i0 + t)
             }
         }
+#undef BLK_EMIT_FIELD
         __syncwarp();
         const int m = min(n - done_e, kSearchMaxIds);
         for (int i = lane; i < m; i += 32) {
@@ -232,7 +259,7 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
     const int N = g.N, P = g.P, sw = P * N + P + 4;
     const int nf = kN == 20 ? 1665 : gg.nf;
     const int fld_words = kN == 20 ? 1668 : gg.fld_words;
-    const int per_warp = gg.warp_smem + 2 * kSearchMaxIds + 8 * kSearchMaxDepth + 64;
+    const int per_warp = search_warp_bytes(gg.warp_smem);
     unsigned char *mine_smem = scratch + static_cast<size_t>(warp) * per_warp;
     uint32_t *fld = reinterpret_cast<uint32_t *>(mine_smem);
     uint16_t *ids = reinterpret_cast<uint16_t *>(mine_smem + gg.warp_smem);
@@ -276,6 +303,8 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
             const int front = BLK_LD(f.node_front + node);
             const double s = BLK_LD(f.node_sum_n + node);
             const int state_slot = f.node_state[node];
+            if (lane < 3)                                   // the state is wanted only if an edge gets opened here: pull its
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pool + static_cast<int64_t>(node) * sw + 32 * lane));   // lines into L1 meanwhile
             if (term) {                                     // terminal states are never expanded (mcts.py:60-62)
                 if (lane < P) my_score = f.node_term_value[static_cast<int64_t>(node) * P + lane];
                 break;
@@ -442,14 +471,15 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
         for (int d = lane; d < len; d += 32) {
             const int e = spath[d];
             const int child = d + 1 < len ? snode[d + 1] : last_child;   // the node the edge led to in THIS simulation
-            const double val = sscore[f.node_mover[child]];
             if (kParallel) {
                 // several warps back up through the same edges: sums, not means, so that atomic adds suffice
+                const double val = sscore[f.node_mover[child]];
                 atomicAdd(f.edge_q + e, val);
                 atomicAdd(f.edge_n + e, 1.0);
                 atomicAdd(f.node_sum_n + snode[d], 1.0);
                 atomicSub(f.edge_vl + e, 1);
             } else {
+                const double val = sscore[f.node_mover[child]];
                 const double nn = f.edge_n[e], qq = f.edge_q[e];
                 const double sn = f.node_sum_n[snode[d]];
                 f.edge_q[e] = __ddiv_rn(__dadd_rn(__dmul_rn(nn, qq), val), __dadd_rn(nn, 1.0));
