@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python tools/profile_all.py --capture --tag r2_v7a --only step_bytes,step_bits,step_indices,step_unaligned,leaf_expand,observe,rollout 2>&1 | tail -3
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2_v7.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-extra > gpurun_out/ncu_bench.log 2>&1
+timeout 900 python tools/profile_all.py --capture --tag r2_v8a --only step_bytes,step_bits,step_indices,step_unaligned,leaf_expand,observe,rollout 2>&1 | tail -3
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2_v8.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-extra > gpurun_out/ncu_bench.log 2>&1
 ls -la gpurun_out | head -20; du -sh gpurun_out
