@@ -1,9 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python bench.py --steps 200 --warmup 10 > gpurun_out/bench_r2_v7_n1.json 2> gpurun_out/bench_r2_v7_n1.err; tail -c 400 gpurun_out/bench_r2_v7_n1.err
-timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_r2_v7_ref.json 2>/dev/null
-timeout 300 python bench.py --workload rollouts --steps 5 > gpurun_out/bench_r2_v7_rollouts_n1.json 2> gpurun_out/bench_r2_v7_w.err
-timeout 300 python bench.py --workload puct --steps 5 > gpurun_out/bench_r2_v7_puct_n1.json 2>> gpurun_out/bench_r2_v7_w.err
-timeout 300 python bench.py --mask bits --steps 200 --no-cpu --no-extra > gpurun_out/bench_r2_v7_bits_n1.json 2>> gpurun_out/bench_r2_v7_w.err
-timeout 300 python bench.py --board 7 --players 2 --envs 1048576 --steps 100 --no-cpu --no-extra > gpurun_out/bench_r2_v7_7x7_n1.json 2>> gpurun_out/bench_r2_v7_w.err
-tail -c 300 gpurun_out/bench_r2_v7_w.err
+timeout 900 python bench.py --steps 200 --warmup 10 > gpurun_out/bench_r2_v8_n1.json 2> gpurun_out/bench_r2_v8_n1.err; tail -c 400 gpurun_out/bench_r2_v8_n1.err
+timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_r2_v8_ref.json 2>/dev/null
+timeout 300 python bench.py --workload rollouts --steps 5 > gpurun_out/bench_r2_v8_rollouts_n1.json 2> gpurun_out/bench_r2_v8_w.err
+timeout 300 python bench.py --workload puct --steps 5 > gpurun_out/bench_r2_v8_puct_n1.json 2>> gpurun_out/bench_r2_v8_w.err
+timeout 300 python bench.py --mask bits --steps 200 --no-cpu --no-extra > gpurun_out/bench_r2_v8_bits_n1.json 2>> gpurun_out/bench_r2_v8_w.err
+timeout 300 python bench.py --board 7 --players 2 --envs 1048576 --steps 100 --no-cpu --no-extra > gpurun_out/bench_r2_v8_7x7_n1.json 2>> gpurun_out/bench_r2_v8_w.err
+tail -c 300 gpurun_out/bench_r2_v8_w.err
