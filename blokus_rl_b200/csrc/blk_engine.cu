@@ -333,21 +333,33 @@ int build_tables(blk_engine *h) {
             for (int y = 0; y < N - kOrient[o].h + 1; ++y) blob[t.off_f2o + f++] = static_cast<unsigned char>(o);
         }
     }
-    // gather descriptors: word g = (fld[s] >> r0) | (fld[s+1] << s1) | (fld[s+2] << s2); shifts >= 32 give 0
-    g.fast3 = 1;
+    // gather descriptors: word g = (fld[s] >> r0) | (fld[s+1] << s1) | (fld[s+2] << s2) [| (fld[s+3] << s3) | (fld[s+4] << s4)];
+    // shifts >= 32 give 0.  Three fields per word suffice at N >= 15 (fields >= 11 bits wide), five at N >= 12.
     std::vector<uint32_t> wdesc(2 * 32 * g.rounds);
-    for (int w = 0; w < 32 * g.rounds; ++w) { wdesc[2 * w] = 4u * g.nf; wdesc[2 * w + 1] = (63u << 8) | (63u << 16); }
-    for (int w = 0; w < g.mw && g.fast3; ++w) {
+    auto start = [&](int f) { return f < g.nf ? static_cast<int>(foff[f]) : (1 << 20); };   // past the last field: never
+    auto clamp63 = [](int v) { return static_cast<uint32_t>(v > 63 ? 63 : v); };
+    g.gather = 0;
+    for (int reach : {3, 5}) {
+        bool fits = true;
+        for (int w = 0; w < g.mw && fits; ++w) {
+            const int s0 = wsrc[w];
+            if (s0 >= g.nf) continue;                   // padding word: gathers the zero slots behind the fields
+            const int r0 = 32 * w - start(s0);
+            fits = start(s0 + reach) >= 32 * w + 32 && r0 >= 0 && r0 <= 31;   // no further field reaches into this word
+        }
+        if (fits) { g.gather = reach; break; }
+    }
+    for (int w = 0; w < 32 * g.rounds; ++w) {
+        wdesc[2 * w] = 4u * g.nf | (g.gather == 5 ? (63u << 16) | (63u << 24) : 0u);
+        wdesc[2 * w + 1] = (63u << 8) | (63u << 16);
+    }
+    for (int w = 0; w < g.mw && g.gather; ++w) {
         const int s0 = wsrc[w];
-        if (s0 >= g.nf) continue;                       // padding word: gathers the zero slots behind the fields
-        auto start = [&](int f) { return f < g.nf ? static_cast<int>(foff[f]) : (1 << 20); };   // past the last field: never
-        if (start(s0 + 3) < 32 * w + 32) { g.fast3 = 0; break; }   // a 4th field reaches into this word
-        const int r0 = 32 * w - start(s0);
-        const int s1 = start(s0 + 1) - 32 * w, s2 = start(s0 + 2) - 32 * w;
-        if (r0 < 0 || r0 > 31) { g.fast3 = 0; break; }
+        if (s0 >= g.nf) continue;
+        const int b = 32 * w;
         wdesc[2 * w] = 4u * static_cast<uint32_t>(s0);
-        wdesc[2 * w + 1] = static_cast<uint32_t>(r0) | (static_cast<uint32_t>(s1 > 63 ? 63 : s1) << 8) |
-                           (static_cast<uint32_t>(s2 > 63 ? 63 : s2) << 16);
+        if (g.gather == 5) wdesc[2 * w] |= (clamp63(start(s0 + 3) - b) << 16) | (clamp63(start(s0 + 4) - b) << 24);
+        wdesc[2 * w + 1] = static_cast<uint32_t>(b - start(s0)) | (clamp63(start(s0 + 1) - b) << 8) | (clamp63(start(s0 + 2) - b) << 16);
     }
     memcpy(blob.data() + kOffWdesc, wdesc.data(), 4 * wdesc.size());
     for (int b = 0; b < 256; ++b) {
@@ -363,10 +375,12 @@ int build_tables(blk_engine *h) {
         const float q[4] = {b & 1 ? 1.f : 0.f, b & 2 ? 1.f : 0.f, b & 4 ? 1.f : 0.f, b & 8 ? 1.f : 0.f};
         memcpy(blob.data() + t.off_obslut + 16 * b, q, 16);
     }
-    g.fld_words = (g.nf + 3 + 3) & ~3;                   // >= nf + 3 zero slots for the gather
+    g.fld_words = (g.nf + (g.gather == 5 ? 5 : 3) + 3) & ~3;   // >= nf + 3 (or 5) zero slots for the gather
+    if (N == 14) g.fld_words = 1152;                     // 32 lanes x 36 fields: the chunked readers use 16 B loads
     g.warp_smem = align16(4 * g.fld_words + 4 * 32);      // fields + 32 per-pass popcount totals (sampler)
-    if (N == 20 && (g.A != 30433 || g.nf != 1665 || g.mw != 952 || g.fld_words != 1668 || !g.fast3))
-        return fail(BLK_ERR_ARG, "internal: N=20 constants in the specialised kernels are stale");
+    if ((N == 20 && (g.A != 30433 || g.nf != 1665 || g.mw != 952 || g.rounds != 30 || g.fld_words != 1668 || g.gather != 3)) ||
+        (N == 14 && (g.A != 13729 || g.nf != 1119 || g.mw != 432 || g.rounds != 14 || g.fld_words != 1152 || g.gather != 5)))
+        return fail(BLK_ERR_ARG, "internal: the geometry constants in the specialised kernels are stale");
     CUDA_TRY(cudaMalloc(&h->d_tables, off));
     CUDA_TRY(cudaMemcpy(h->d_tables, blob.data(), off, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned long long) * 2 * kQueueSlots));

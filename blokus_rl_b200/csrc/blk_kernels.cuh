@@ -76,8 +76,9 @@ struct TableLayout {
     int roll_begin;  // the rollout kernel stages only [roll_begin, bytes): oinfo, ocells, foff, fbase, f2o
     // Two tables sit at FIXED offsets so their shared-memory addresses are immediates in the unrolled emit loop:
     //   kOffLut   = 0     uint2[256]        byte -> 8 bytes of 0/1 (bit i -> byte i)
-    //   kOffWdesc = 2048  uint2[32*rounds]  gather descriptor of mask word g (valid when <= 3 fields meet a word):
+    //   kOffWdesc = 2048  uint2[32*rounds]  gather descriptor of mask word g (valid when <= 3 or <= 5 fields meet a word):
     //                     .x = byte offset of the first field in the staging area
+    //                          (Geometry::gather == 5: | left shift of field 3 << 16 | left shift of field 4 << 24)
     //                     .y = right shift of field 0 | left shift of field 1 << 8 | left shift of field 2 << 16
 };
 
@@ -87,8 +88,19 @@ struct Geometry {
     int warp_smem;      // bytes of per-warp scratch (fields + per-word popcounts)
     int fld_words;      // >= nf + 3; words nf..nf+2 stay zero (gather padding)
     int rounds;         // ceil(mw / 32): warp-wide passes over the mask words
-    int fast3;          // 1 when every mask word gathers from <= 3 fields (true at N = 20)
+    int gather;         // 3 / 5: every mask word gathers from at most that many fields (3 at N = 20, 5 at N = 12..14), so the
+                        // branch-free descriptors apply; 0: the generic loop
 };
+
+// The geometries with their own instantiation carry these as immediates (checked against the tables at blk_create).
+template <int kN> __device__ __forceinline__ int geo_nf(const Geometry &g) { return kN == 20 ? 1665 : kN == 14 ? 1119 : g.nf; }
+template <int kN> __device__ __forceinline__ int geo_fld_words(const Geometry &g) { return kN == 20 ? 1668 : kN == 14 ? 1152 : g.fld_words; }
+template <int kN> __device__ __forceinline__ int geo_mw(const Geometry &g) { return kN == 20 ? 952 : kN == 14 ? 432 : g.mw; }
+template <int kN> __device__ __forceinline__ int geo_rounds(const Geometry &g) { return kN == 20 ? 30 : kN == 14 ? 14 : g.rounds; }
+template <int kN> __device__ __forceinline__ int geo_gather(const Geometry &g) { return kN == 20 ? 3 : kN == 14 ? 5 : g.gather; }
+// contiguous fields per lane when the legal set is read straight from the fields: 52 (+1 for lane 31) at N = 20,
+// 36 at N = 14 (32 x 36 = 1152 = the padded staging area), otherwise ceil(nf / 32)
+template <int kN> __device__ __forceinline__ int fields_per_lane(int nf) { return kN == 20 ? 53 : kN == 14 ? 36 : (nf + 31) >> 5; }
 
 struct KParams {
     blk_step_args a;
@@ -440,6 +452,15 @@ __device__ __forceinline__ uint32_t assemble_word3(int g, const uint32_t *fld, c
            shl_clamp(p[2], __byte_perm(d.y, 0u, 0x4442u));
 }
 
+// ... and its five-field form (N = 12..14: fields are 8-14 bits wide); the two extra shifts ride in the upper half of .x
+__device__ __forceinline__ uint32_t assemble_word5(int g, const uint32_t *fld, const uint2 *wdesc) {
+    const uint2 d = wdesc[g];
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(fld) + (d.x & 0xffffu));
+    return __funnelshift_r(p[0], 0u, d.y) | shl_clamp(p[1], __byte_perm(d.y, 0u, 0x4441u)) |
+           shl_clamp(p[2], __byte_perm(d.y, 0u, 0x4442u)) | shl_clamp(p[3], __byte_perm(d.x, 0u, 0x4442u)) |
+           shl_clamp(p[4], __byte_perm(d.x, 0u, 0x4443u));
+}
+
 struct SmemTables {
     const int32_t *obase;
     const uint32_t *oinfo;
@@ -588,6 +609,13 @@ __device__ __forceinline__ int count_field_chunk(const uint32_t *fld, int nf, in
             mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
         }
         if (lane == 31) mine += __popc(fld[1664]);
+    } else if (kN == 14) {          // 1119 fields in a zero-padded area of 32 x 36 words: 9 conflict-free LDS.128 per lane
+        const uint4 *f4 = reinterpret_cast<const uint4 *>(fld) + 9 * lane;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const uint4 x = f4[j];
+            mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+        }
     } else {
         for (int j = 0; j < per; ++j) { const int i = lane * per + j; if (i < nf) mine += __popc(fld[i]); }
     }
@@ -638,11 +666,12 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = g.N, P = g.P;
     const int sw = P * N + P + 4;
-    const int fld_words = kN == 20 ? 1668 : gg.fld_words;
-    const int mw = kN == 20 ? 952 : gg.mw;
-    const int rounds = kN == 20 ? 30 : gg.rounds;
-    const int mask_bytes = kN == 20 ? (30433 + BLK_ROW_ALIGN - 1) / BLK_ROW_ALIGN * BLK_ROW_ALIGN : gg.mask_bytes;
-    const bool fast3 = kN == 20 ? true : (gg.fast3 != 0);
+    const int fld_words = geo_fld_words<kN>(gg);
+    const int mw = geo_mw<kN>(gg);
+    const int rounds = geo_rounds<kN>(gg);
+    const int mask_bytes = kN == 20 ? (30433 + BLK_ROW_ALIGN - 1) / BLK_ROW_ALIGN * BLK_ROW_ALIGN
+                         : kN == 14 ? (13729 + BLK_ROW_ALIGN - 1) / BLK_ROW_ALIGN * BLK_ROW_ALIGN : gg.mask_bytes;
+    const int gather = geo_gather<kN>(gg);
     uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * gg.warp_smem);
     uint32_t *tots = fld + fld_words;                                  // 32 per-pass popcount totals (sampler)
     const int64_t n = a.n;
@@ -652,7 +681,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
     const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);
     const unsigned char *lutb = reinterpret_cast<const unsigned char *>(tb.lut);
     const uint2 *wdl = tb.wdesc + lane;
-    for (int i = (kN == 20 ? 1665 : gg.nf) + lane; i < fld_words; i += 32) fld[i] = 0u;   // gather padding stays zero
+    for (int i = geo_nf<kN>(gg) + lane; i < fld_words; i += 32) fld[i] = 0u;   // gather padding stays zero
 
     // software pipeline over this warp's envs: the next env's 352 B and action are fetched while the current one
     // is processed (a warp handles its envs serially; without this every env starts with an exposed HBM round trip)
@@ -740,8 +769,8 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
             // Index list: the ids come straight out of the fields (field order is id order), no mask words are built.
             // Every lane counts its contiguous chunk of fields, a scan gives it its first slot, and it writes its ids there.
             // (The mask-word route -- 30 passes of gather + scan + per-lane bit loops -- cost 4,500 warp instructions per env.)
-            const int nf_ = kN == 20 ? 1665 : gg.nf;
-            const int per = (nf_ + 31) >> 5;
+            const int nf_ = geo_nf<kN>(gg);
+            const int per = fields_per_lane<kN>(nf_);
             const int mine = count_field_chunk<kN>(fld, nf_, per, lane);
             const int incl = warp_incl_scan(mine, lane);
             cnt = __shfl_sync(kAllLanes, incl, 31);
@@ -793,9 +822,10 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
             const int ush = static_cast<int>(reinterpret_cast<uintptr_t>(urow) & 15);
             uint32_t uprev = 0u;
 #pragma unroll(kEmitUnroll)
-            for (int r = 0; r < (kN == 20 ? 30 : rounds); ++r) {
+            for (int r = 0; r < rounds; ++r) {
                 uint32_t word;
-                if (fast3) word = assemble_word3(r << 5, fld, wdl);
+                if (gather == 3) word = assemble_word3(r << 5, fld, wdl);
+                else if (gather == 5) word = assemble_word5(r << 5, fld, wdl);
                 else word = ((r << 5) + lane) < mw ? assemble_word((r << 5) + lane, fld, tb.foff, tb.wsrc) : 0u;
                 const int pc = __popc(word);
                 if (kSample) {
@@ -808,7 +838,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                 if (kFmt == 4) {
                     // (handled above, straight from the fields)
                 } else if (kFmt == 1) {
-                    if (r < (kN == 20 ? 29 : rounds - 1) || (r << 5) + lane < mw) wrow[r << 5] = word;
+                    if (r < rounds - 1 || (r << 5) + lane < mw) wrow[r << 5] = word;
                 } else if (kFmt == 2) {
                     // 32 words -> 1024 bytes; each lane expands 16 bits through the byte LUT (two 8-byte entries) and
                     // writes 16 B, so one warp store covers 512 contiguous bytes
@@ -818,7 +848,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                         const uint2 lo = *reinterpret_cast<const uint2 *>(lutb + (__funnelshift_l(w2, w2, rot_lo) & 0x7f8u));
                         const uint2 hi = *reinterpret_cast<const uint2 *>(lutb + (__funnelshift_l(w2, w2, rot_hi) & 0x7f8u));
                         const int boff = (r << 10) + 512 * h;
-                        if (r < (kN == 20 ? 29 : rounds - 1) || boff + 16 * lane < mask_bytes)
+                        if (r < rounds - 1 || boff + 16 * lane < mask_bytes)
                             BLK_STORE16(reinterpret_cast<uint4 *>(row + boff), make_uint4(lo.x, lo.y, hi.x, hi.y));
                     }
                 } else if (kFmt == 3) {
@@ -871,7 +901,8 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                 // level 2: which word of that pass (re-gathered: cheaper than keeping 952 popcounts around)
                 const int gi = (R << 5) + lane;
                 uint32_t word;
-                if (fast3) word = assemble_word3(gi, fld, tb.wdesc);
+                if (gather == 3) word = assemble_word3(gi, fld, tb.wdesc);
+                else if (gather == 5) word = assemble_word5(gi, fld, tb.wdesc);
                 else word = gi < mw ? assemble_word(gi, fld, tb.foff, tb.wsrc) : 0u;
                 const int c2 = __popc(word);
                 const int incl2 = warp_incl_scan(c2, lane);
@@ -915,8 +946,8 @@ __device__ __forceinline__ int playout_game(EnvRegs &e, const SmemTables &tb, co
                                             int lane, uint32_t key0, uint32_t key1, uint32_t stream, int stop_player,
                                             uint16_t *log, int log_cap, bool &over) {
     const int N = g.N, P = g.P;
-    const int nf = kN == 20 ? 1665 : gg.nf;
-    const int per = (nf + 31) >> 5;   // contiguous fields per lane for the k-th-bit search (53 at N = 20)
+    const int nf = geo_nf<kN>(gg);
+    const int per = fields_per_lane<kN>(nf);   // contiguous fields per lane for the k-th-bit search (53 at N = 20)
     int nply = 0;
     uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
     int rnd_block = -1;

@@ -135,7 +135,7 @@ __device__ __forceinline__ int node_create(const blk_puct_forest &f, uint32_t *p
 template <int kN, bool kFence>
 __device__ __forceinline__ bool expand_from_fields(const blk_puct_forest &f, int node, const uint32_t *fld, uint16_t *ids,
                                                    const SmemTables &tb, int nf, int lane) {
-    const int per = (nf + 31) >> 5;
+    const int per = fields_per_lane<kN>(nf);
     const int mine = count_field_chunk<kN>(fld, nf, per, lane);       // lane l owns fields [l * chunk, + len): 13 LDS.128 at N = 20
     const int chunk = kN == 20 ? 52 : per;
     const int i0 = lane * chunk;
@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = g.N, P = g.P, sw = P * N + P + 4;
-    const int nf = kN == 20 ? 1665 : gg.nf;
-    const int fld_words = kN == 20 ? 1668 : gg.fld_words;
+    const int nf = geo_nf<kN>(gg);
+    const int fld_words = geo_fld_words<kN>(gg);
     const int per_warp = search_warp_bytes(gg.warp_smem);
     unsigned char *mine_smem = scratch + static_cast<size_t>(warp) * per_warp;
     uint32_t *fld = reinterpret_cast<uint32_t *>(mine_smem);
@@ -315,8 +315,8 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
                     int old = -1;
                     if (lane == 0) old = (e0 == -1) ? atomicCAS(f.node_edge0 + node, -1, -2) : e0;
                     old = __shfl_sync(kAllLanes, old, 0);
-                    if (old != -1) {                        // somebody else is expanding it: wait for the edges
-                        while (ld_volatile(f.node_edge0 + node) < 0) __nanosleep(100);
+                    if (old != -1) {                        // somebody else is expanding it: wait until it has edges (or was
+                        while (ld_volatile(f.node_edge0 + node) == -2) __nanosleep(100);   // handed back unexpanded: -1)
                         __threadfence();
                         --depth;
                         continue;
@@ -329,11 +329,20 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
                 prep_rows(e, mv, g, lane, fr0, dg0);
                 eval_fields<true, false>(fr0, dg0, sel4(e.inv0, e.inv1, e.inv2, e.inv3, mv), fld, N, lane);
                 __syncwarp();
-                if (!expand_from_fields<kN, kParallel>(f, node, fld, ids, tb, nf, lane)) break;
+                if (!expand_from_fields<kN, kParallel>(f, node, fld, ids, tb, nf, lane)) {
+                    // edge arrays full (flagged in counters[2]): hand the node back unexpanded so that nobody waits for it
+                    if (kParallel) BLK_PUBLISH(f.node_edge0 + node, -1);
+                    break;
+                }
                 my_score = leaf_value<kN, kP>(sp, e, node, tb, g, fld, lane);
                 break;
             }
             if (len >= max_depth) { if (lane == 0) f.counters[2] = 1; break; }
+            if (kParallel && n <= 0) {                      // edge0 was already visible, the edge count not yet: read the header again
+                __threadfence();
+                --depth;
+                continue;
+            }
             // ---- selection: U = c * P * sqrt(sum N + eps) / (1 + N), first maximum of Q + U (mcts.py:42-46) ----
             const double pu = __ddiv_rn(1.0, static_cast<double>(n));
             const double c = depth == 0 ? sp.a.cpuct : 1.0;
@@ -399,8 +408,13 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
                 }
             }
             if (child == -2) {                              // another warp is opening this edge
-                while ((child = ld_volatile(f.edge_child + e)) < 0) __nanosleep(100);
+                while ((child = ld_volatile(f.edge_child + e)) == -2) __nanosleep(100);
                 __threadfence();
+                if (child < 0) {                            // the opener gave up (node pool exhausted: flagged): so does this simulation
+                    if (lane == 0) atomicSub(f.edge_vl + e, 1);
+                    --len;
+                    break;
+                }
             }
             if (child >= 0) { node = last_child = child; continue; }
             // ---- open the edge: env transition of the parent's state under the edge's action ----
@@ -461,6 +475,7 @@ __global__ void __launch_bounds__(kParallel ? 512 : kSearchTrees * 32) puct_sear
                 break;
             }
             const bool ok = expand_from_fields<kN, kParallel>(f, fresh, fld, ids, tb, nf, lane);
+            if (kParallel && !ok) BLK_PUBLISH(f.node_edge0 + fresh, -1);     // edge arrays full: nobody may wait for these edges
             BLK_PUBLISH(f.edge_child + e, fresh);
             if (ok) my_score = leaf_value<kN, kP>(sp, es, fresh, tb, g, fld, lane);
             break;

@@ -22,7 +22,7 @@ class Guarded:
         assert bool((self.raw[-BAND:] == FILL).all()), f"{what}: wrote behind the buffer"
 
 
-@pytest.mark.parametrize("N,P", [(20, 4), (20, 2), (14, 4), (7, 2), (7, 4), (9, 2)])
+@pytest.mark.parametrize("N,P", [(20, 4), (20, 2), (14, 4), (14, 2), (12, 2), (7, 2), (7, 4), (9, 2)])
 def test_step_outputs_stay_inside_their_buffers(N, P):
     from blokus_rl_b200 import BlokusEngine
     from blokus_rl_b200.engine import StepOut

@@ -55,7 +55,7 @@ def test_lockstep_7x7_2p(engine7, oracle7):
     assert games > 64
 
 
-@pytest.mark.parametrize("n,p", [(14, 2), (14, 4), (7, 4), (5, 2), (20, 2)])
+@pytest.mark.parametrize("n,p", [(14, 2), (14, 4), (7, 4), (5, 2), (20, 2), (12, 4), (13, 2), (15, 2), (10, 2)])   # 12-15: five-field gather descriptors; 10: the generic gather
 def test_lockstep_other_geometries(n, p):
     from blokus_rl_b200 import BlokusEngine
     from oracle.oracle import Oracle
