@@ -9,26 +9,57 @@ run them over a CPU-oracle backend inside the build container (no GPU there) —
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
-from ._lib import BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED
+from . import _lib
+from ._lib import BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED, BLK_MASK_INDICES
 from .engine import BlokusEngine, StepOut
+
+
+def _cudart():
+    """libcudart as this process already has it (torch loads it), for cudaMemcpyAsync / cudaStreamSynchronize without the
+    5-15 us of Python wrapping per call; None when it cannot be found by name (the torch calls are used then)."""
+    for name in ("libcudart.so.12", "libcudart.so"):
+        try:
+            rt = C.CDLL(name)
+            rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+            rt.cudaMemcpyAsync.restype = C.c_int
+            rt.cudaStreamSynchronize.argtypes = [C.c_void_p]
+            rt.cudaStreamSynchronize.restype = C.c_int
+            return rt
+        except (OSError, AttributeError):
+            continue
+    return None
 
 
 class StateHandle:
     """Immutable env state: device words + the host copy of everything the step that produced it returned."""
-    __slots__ = ("words", "host_words", "ids", "_mask", "flags", "terminal", "scores", "_obs", "_board")
+    __slots__ = ("_pack", "_words", "_sw", "host_words", "ids", "_mask", "flags", "terminal", "scores", "_obs", "_board")
 
-    def __init__(self, words, host_words, ids, flags, terminal, scores):
-        self.words, self.host_words, self.ids = words, host_words, ids
+    def __init__(self, words, host_words, ids, flags, terminal, scores, obs=None, pack=None, sw=0):
+        self._words, self._pack, self._sw = words, pack, sw
+        self.host_words, self.ids = host_words, ids
         self.flags, self.terminal, self.scores = flags, terminal, scores
-        self._mask = self._obs = self._board = None
+        self._mask = self._board = None
+        self._obs = obs
+
+    @property
+    def words(self) -> torch.Tensor:
+        """The state on the device, int32 [1, state_words] (the head of the buffer the transition wrote)."""
+        if self._words is None:
+            self._words = self._pack[: 4 * self._sw].view(torch.int32).view(1, self._sw)
+        return self._words
 
 
 class EngineBackend:
     def __init__(self, board_size: int = 20, num_players: int = 4, score_rule: int = 0, device=None,
-                 engine: BlokusEngine | None = None):
+                 engine: BlokusEngine | None = None, fuse_observation: bool = True):
+        """``fuse_observation``: every transition also writes the new state's ``canonical_board`` planes (from the same
+        launch, into the same buffer), so the ``get_observation`` that follows each expansion of the reference's search
+        (mcts.py:60-66) costs no second launch.  12.8 KB more per device-to-host copy at 20x20 / 4 players."""
         self.eng = engine if engine is not None else BlokusEngine(board_size, num_players, score_rule, device)
         self.N, self.P, self.A = self.eng.board_size, self.eng.num_players, self.eng.num_actions
         self._meta = self.P * self.N + self.P
@@ -42,7 +73,29 @@ class EngineBackend:
         self._o_count = self._o_score + 16
         self._o_flags = self._o_count + 4
         self._o_ids = a16(self._o_flags + 1)
-        self._pack_bytes = self._o_ids + 2 * self.eng.max_legal
+        self._o_obs = a16(self._o_ids + 2 * self.eng.max_legal)
+        self._obs_floats = 2 * self.P * self.N * self.N if fuse_observation else 0
+        self._pack_bytes = self._o_obs + 4 * self._obs_floats
+        # The per-move path (`next_state`: 25-200 calls per move of the reference's search) goes to the C ABI directly: the
+        # argument block is filled once, the action is read by the kernel from pinned host memory (no H2D copy call), and
+        # the outputs come back through one async copy into a pinned buffer + one stream synchronize.
+        dev = self.eng.device
+        self._direct = isinstance(self.eng, BlokusEngine)     # (the host-logic tests drive this class over a stand-in engine)
+        if not self._direct:
+            return
+        self._act = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._act_np = self._act.numpy()
+        self._host = torch.empty(self._pack_bytes, dtype=torch.uint8).pin_memory()
+        self._host_np = self._host.numpy()
+        self._args = _lib.BlkStepArgs(1, None, None, self._act.data_ptr(), None, BLK_MASK_INDICES, self.eng.max_legal,
+                                      None, None, None, None, None, 0, 0, 0, None, None, None, None)
+        self._args_ref = C.byref(self._args)
+        self._step = self.eng._lib.blk_step
+        self._dev_index = dev.index
+        self._host_ptr = C.c_void_p(self._host.data_ptr())
+        self._cudart = _cudart()
+        with torch.cuda.device(dev):
+            self._fetched = torch.cuda.Event()
 
     # ---- construction ------------------------------------------------------------------------------
     def _views(self, pack: torch.Tensor):
@@ -53,7 +106,7 @@ class EngineBackend:
                        pack[self._o_term: self._o_term + 4 * P].view(torch.float32).view(1, P),
                        pack[self._o_flags: self._o_flags + 1],
                        pack[self._o_score: self._o_score + 2 * P].view(torch.int16).view(1, P), None)
-        ids = pack[self._o_ids:].view(torch.int16).view(1, self.eng.max_legal)
+        ids = pack[self._o_ids: self._o_ids + 2 * self.eng.max_legal].view(torch.int16).view(1, self.eng.max_legal)
         return words, bufs, ids
 
     def _transition(self, src: torch.Tensor, action: torch.Tensor | None) -> StateHandle:
@@ -83,12 +136,56 @@ class EngineBackend:
         s = torch.from_numpy(np.ascontiguousarray(words, np.uint32).view(np.int32).reshape(1, -1)).to(self.eng.device)
         return self._transition(s, None)
 
+    def _launch_and_fetch(self, pack: torch.Tensor) -> None:
+        stream = self.eng._stream()
+        _lib.check(self._step(self.eng._h, self._args_ref, stream))
+        rt = self._cudart
+        if rt is not None:                               # the CUDA runtime torch already loaded, called directly
+            if rt.cudaMemcpyAsync(self._host_ptr, C.c_void_p(pack.data_ptr()), self._pack_bytes, 2, stream) or \
+                    rt.cudaStreamSynchronize(stream):
+                raise _lib.EngineError("device-to-host copy of a transition failed")
+            return
+        self._host.copy_(pack, non_blocking=True)
+        self._fetched.record()
+        self._fetched.synchronize()
+
     def next_state(self, h: StateHandle, action_id: int) -> StateHandle:
-        act = torch.tensor([int(action_id)], dtype=torch.int32).to(self.eng.device, non_blocking=True)
-        nh = self._transition(h.words, act)
-        if nh.flags & BLK_FLAG_ILLEGAL:
+        if not self._direct:
+            act = torch.tensor([int(action_id)], dtype=torch.int32).to(self.eng.device, non_blocking=True)
+            nh = self._transition(h.words, act)
+            if nh.flags & BLK_FLAG_ILLEGAL:
+                raise ValueError(f"illegal action {action_id} for player {self.mover(h)}")
+            return nh
+        eng, a, host = self.eng, self._args, self._host_np
+        pack = torch.empty(self._pack_bytes, dtype=torch.uint8, device=eng.device)
+        base = pack.data_ptr()
+        self._act_np[0] = action_id
+        a.state_in = h._pack.data_ptr() if h._pack is not None else h.words.data_ptr()
+        a.state_out = base
+        a.mask = base + self._o_ids
+        a.legal_count = base + self._o_count
+        a.terminal = base + self._o_term
+        a.flags = base + self._o_flags
+        a.scores = base + self._o_score
+        a.obs = base + self._o_obs if self._obs_floats else None
+        if torch.cuda.current_device() == self._dev_index:
+            self._launch_and_fetch(pack)
+        else:
+            with torch.cuda.device(self._dev_index):
+                self._launch_and_fetch(pack)
+        flags = int(host[self._o_flags])
+        if flags & BLK_FLAG_ILLEGAL:
             raise ValueError(f"illegal action {action_id} for player {self.mover(h)}")
-        return nh
+        if flags & BLK_FLAG_TRUNCATED:                                     # more legal moves than the id row holds: general path
+            return self._transition(pack[: 4 * eng.state_words].view(torch.int32).view(1, eng.state_words), None)
+        n = int(host[self._o_count: self._o_count + 4].view(np.int32)[0])
+        P = self.P
+        obs = (host[self._o_obs: self._o_obs + 4 * self._obs_floats].view(np.float32).reshape(2 * P, self.N, self.N).copy()
+               if self._obs_floats else None)
+        return StateHandle(None, host[: 4 * eng.state_words].view(np.uint32).copy(),
+                           host[self._o_ids: self._o_ids + 2 * n].view(np.uint16).astype(np.int64), flags,
+                           host[self._o_term: self._o_term + 4 * P].view(np.float32).copy(),
+                           host[self._o_score: self._o_score + 2 * P].view(np.int16).copy(), obs, pack, eng.state_words)
 
     # ---- queries -------------------------------------------------------------------------------------
     def mover(self, h: StateHandle) -> int:

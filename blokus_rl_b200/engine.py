@@ -43,6 +43,10 @@ class RolloutOut:
     action_log: torch.Tensor | None      # int32-viewable uint16 stored as int16 [n_roots, per_root, log_stride]
 
 
+# the current stream's handle without building a torch.cuda.Stream object (9 us -> < 1 us per launch)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (lambda index: torch.cuda.current_stream(index).cuda_stream)
+
+
 def _ptr(t: torch.Tensor | None):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -88,7 +92,7 @@ class BlokusEngine:
 
     # ------------------------------------------------------------------------------------------
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(_raw_stream(self.device.index))
 
     def _check_states(self, states: torch.Tensor):
         if states.dtype != torch.int32 or states.dim() != 2 or states.shape[1] != self.state_words \
