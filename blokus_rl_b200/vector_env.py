@@ -24,10 +24,13 @@ from index lists (it is produced on first use after a step).
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
-from ._lib import BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED
+from . import _lib
+from ._lib import BLK_FLAG_ILLEGAL, BLK_FLAG_TRUNCATED, BLK_MASK_INDICES, BLK_MASK_NONE
 
 
 class _Box:
@@ -67,20 +70,49 @@ class BlokusVectorEnv:
         self._epoch = 0
         # sparse legal ids of the agent: row width grows when a position has more legal moves than fit
         self._idx_stride = 128 if self.N <= 7 else 512
+        # `step` on the real engine goes to the C ABI directly (argument blocks filled once, one staging copy back): at the
+        # reference's default of 4 envs a step is launch-latency-bound, and ~40 torch calls cost 4x what the kernels do
+        from .engine import BlokusEngine
+        self._direct = isinstance(engine, BlokusEngine)
         self._alloc_idx()
         self._ids_host = None              # (counts, ids) of the current states on the host, filled on demand
-        self._h_board, self._h_reward = self._host((num_envs, self.N, self.N), torch.uint8), self._host(num_envs, torch.float32)
+        self._h_reward = self._host(num_envs, torch.float32)
         self._h_done = self._host(num_envs, torch.bool)
         self._h_fret, self._h_flen = self._host(num_envs, torch.float32), self._host(num_envs, torch.int64)
-        self._h_fobs = self._host((num_envs, self.N, self.N), torch.uint8)
+        self._np_ep_len = np.zeros(num_envs, np.int64)          # episode statistics of the NumPy surface (`step`)
+        self._np_ep_ret = np.zeros(num_envs, np.float32)
+        if self._direct:
+            self._h_acts = self._host(num_envs, torch.int32)
+            self._d_acts = torch.empty(num_envs, dtype=torch.int32, device=dev)
+            self._cudart = _cudart()
+            self._args_a = _lib.BlkStepArgs(num_envs, None, None, self._d_acts.data_ptr(), None, BLK_MASK_NONE, 0, None, None, None,
+                                            None, None, 0, 0, 0, None, None, None, None)
+            self._args_i = _lib.BlkStepArgs(num_envs, None, None, None, None, BLK_MASK_INDICES, 0, None, None, None,
+                                            None, None, 0, 0, 0, None, None, None, None)
+            self._rargs = _lib.BlkRolloutArgs(num_envs, None, 1, 0, 0, None, None, None, None, 88, None, int(self.agent), None, 0)
 
     def _alloc_idx(self):
-        E, dev = self.num_envs, self.eng.device
-        self._idx = torch.empty((E, self._idx_stride), dtype=torch.int16, device=dev)
-        self._cnt = torch.empty(E, dtype=torch.int32, device=dev)
-        self._idx_flags = torch.empty(E, dtype=torch.uint8, device=dev)
-        self._h_idx, self._h_cnt = self._host((E, self._idx_stride), torch.int16), self._host(E, torch.int32)
-        self._h_idx_flags = self._host(E, torch.uint8)
+        """One device buffer and one (pinned) host buffer hold everything a step returns, so it comes back in ONE copy:
+        flags of the agent's move | winners of finished games | flags of the id launch | legal counts | final board cells |
+        board cells | legal ids (``_idx_stride`` per env; grows when a position has more legal moves)."""
+        E, dev, NN = self.num_envs, self.eng.device, self.N * self.N
+        a16 = lambda x: (x + 15) & ~15
+        o_fa, o_win, o_if = 0, a16(E), 2 * a16(E)
+        o_cnt = 3 * a16(E)
+        o_fobs = a16(o_cnt + 4 * E)
+        o_obs = a16(o_fobs + E * NN)
+        o_idx = a16(o_obs + E * NN)
+        self._pack_bytes = o_idx + 2 * E * self._idx_stride
+        self._dpack = torch.zeros(self._pack_bytes, dtype=torch.uint8, device=dev)
+        self._hpack = self._host(self._pack_bytes, torch.uint8)
+
+        def carve(pack):
+            return (pack[o_fa: o_fa + E], pack[o_win: o_win + E], pack[o_if: o_if + E],
+                    pack[o_cnt: o_cnt + 4 * E].view(torch.int32), pack[o_fobs: o_fobs + E * NN].view(E, self.N, self.N),
+                    pack[o_obs: o_obs + E * NN].view(E, self.N, self.N),
+                    pack[o_idx:].view(torch.int16).view(E, self._idx_stride))
+        self._d_flags_a, self._d_win, self._idx_flags, self._cnt, self._d_fobs, self._d_obs, self._idx = carve(self._dpack)
+        self._h_flags_a, self._h_win, self._h_idx_flags, self._h_cnt, self._h_fobs, self._h_board, self._h_idx = carve(self._hpack)
 
     def _host(self, shape, dtype):
         # pinned staging memory (the CPU stand-in engine of the host-logic tests has none)
@@ -131,6 +163,8 @@ class BlokusVectorEnv:
         self.states = self.eng.new_states(self.num_envs)
         self._ep_len.zero_()
         self._ep_ret.zero_()
+        self._np_ep_len[:] = 0
+        self._np_ep_ret[:] = 0
         if self.agent != 0:
             self._play_opponents()
         self._mask = self._ids_host = None
@@ -166,7 +200,81 @@ class BlokusVectorEnv:
             self._play_opponents()
         return self._obs(), reward, done, (fin_ret, fin_len, final_obs)
 
+    def _step_direct(self, actions):
+        """`step` on the CUDA engine: the same launches as `step_device` + `_launch_ids`, issued through the C ABI with
+        prefilled argument blocks into the scratch state buffer, one copy back, one synchronize; committed only when every
+        action was legal.  Rewards and episode statistics are kept on the host (they are E numbers)."""
+        eng, E, lib = self.eng, self.num_envs, self.eng._lib
+        self._h_acts.numpy()[:] = np.asarray(actions)
+        S, T = self.states, self._next
+        tp = T.data_ptr()
+        with torch.cuda.device(eng.device):
+            st = eng._stream()
+            self._d_acts.copy_(self._h_acts, non_blocking=True)
+            a, i, r = self._args_a, self._args_i, self._rargs
+            a.state_in, a.state_out, a.flags = S.data_ptr(), tp, self._d_flags_a.data_ptr()
+            _lib.check(lib.blk_step(eng._h, C.byref(a), st))
+            # random bots move until it is the agent's turn or the game is over; `winners` != 0 marks the finished games
+            r.roots = r.state_out = tp
+            r.winners = self._d_win.data_ptr()
+            r.seed = (self.seed + self._epoch + 1) & 0xFFFFFFFFFFFFFFFF
+            _lib.check(lib.blk_rollout(eng._h, C.byref(r), st))
+            _lib.check(lib.blk_board_contents(eng._h, tp, self._d_fobs.data_ptr(), E, st))
+            # gymnasium-0.29 autoreset: finished envs restart at once
+            torch.where(self._d_win.bool()[:, None], self._fresh, T, out=T)
+            epochs = 1
+            if self.agent != 0:
+                r.winners = None
+                r.seed = (self.seed + self._epoch + 2) & 0xFFFFFFFFFFFFFFFF
+                _lib.check(lib.blk_rollout(eng._h, C.byref(r), st))
+                epochs = 2
+            i.state_in = i.state_out = tp
+            i.mask, i.mask_stride = self._idx.data_ptr(), self._idx_stride
+            i.legal_count, i.flags = self._cnt.data_ptr(), self._idx_flags.data_ptr()
+            _lib.check(lib.blk_step(eng._h, C.byref(i), st))
+            _lib.check(lib.blk_board_contents(eng._h, tp, self._d_obs.data_ptr(), E, st))
+            rt = self._cudart
+            if rt is not None:
+                if rt.cudaMemcpyAsync(self._hpack.data_ptr(), self._dpack.data_ptr(), self._pack_bytes, 2, st) or \
+                        rt.cudaStreamSynchronize(st):
+                    raise _lib.EngineError("device-to-host copy of a vector-env step failed")
+            else:
+                self._hpack.copy_(self._dpack, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        if (self._h_flags_a.numpy() & BLK_FLAG_ILLEGAL).any():
+            self._ids_host = None                          # the staging buffer now holds the abandoned step's ids
+            raise ValueError("illegal action passed to BlokusVectorEnv.step")          # nothing was committed
+        self.states, self._next = T, S
+        self._epoch += epochs
+        self._mask = None
+        win = self._h_win.numpy()
+        done = win != 0
+        mine = (win >> self.agent) & 1
+        reward = np.where(done, np.where(mine != 0, np.where((win & (win - 1)) == 0, 1.0, 0.0), -1.0), 0.0).astype(np.float32)
+        self._np_ep_len += 1
+        self._np_ep_ret += reward
+        obs = self._h_board.numpy().astype(np.float32)
+        info = {}
+        idx = np.flatnonzero(done)
+        if len(idx):
+            fo = self._h_fobs.numpy()
+            final_info = np.full(E, None, dtype=object)
+            final_obs_h = np.full(E, None, dtype=object)
+            for j in idx:
+                final_info[j] = {"episode": {"r": float(self._np_ep_ret[j]), "l": int(self._np_ep_len[j])}}
+                final_obs_h[j] = fo[j].astype(np.float32)
+            info = {"final_info": final_info, "final_observation": final_obs_h, "_final_info": done.copy()}
+            self._np_ep_len[idx] = 0
+            self._np_ep_ret[idx] = 0
+        if (self._h_idx_flags.numpy() & BLK_FLAG_TRUNCATED).any():
+            self._collect_ids()                                    # widens the id rows (new staging buffers) and asks again
+        else:
+            self._ids_host = (self._h_cnt.numpy(), self._h_idx.numpy().view(np.uint16))
+        return obs, reward, done, np.zeros(E, dtype=bool), info
+
     def step(self, actions):
+        if self._direct:
+            return self._step_direct(actions)
         acts = torch.as_tensor(np.asarray(actions), dtype=torch.int32).to(self.eng.device, non_blocking=True)
         obs, reward, done, (fin_ret, fin_len, final_obs) = self.step_device(acts)
         # one round trip: board cells, rewards, done flags, episode statistics and the agent's next legal ids travel together
@@ -175,20 +283,21 @@ class BlokusVectorEnv:
             dst.copy_(src, non_blocking=True)
         self._launch_ids()
         self._sync()
-        self._collect_ids()
+        board_h = self._h_board.numpy().astype(np.float32)
+        fo = self._h_fobs.numpy().copy()
+        self._collect_ids()                                # (may replace the staging buffers: board cells were read first)
         done_h = self._h_done.numpy().copy()
         info = {}
         idx = np.flatnonzero(done_h)
         if len(idx):                                       # gymnasium-0.29 autoreset bookkeeping, only for the envs that finished
-            r, l, fo = self._h_fret.numpy(), self._h_flen.numpy(), self._h_fobs.numpy()
+            r, l = self._h_fret.numpy(), self._h_flen.numpy()
             final_info = np.full(self.num_envs, None, dtype=object)
             final_obs_h = np.full(self.num_envs, None, dtype=object)
             for i in idx:
                 final_info[i] = {"episode": {"r": float(r[i]), "l": int(l[i])}}
                 final_obs_h[i] = fo[i].astype(np.float32)
             info = {"final_info": final_info, "final_observation": final_obs_h, "_final_info": done_h.copy()}
-        return (self._h_board.numpy().astype(np.float32), self._h_reward.numpy().copy(), done_h,
-                np.zeros(self.num_envs, dtype=bool), info)
+        return (board_h, self._h_reward.numpy().copy(), done_h, np.zeros(self.num_envs, dtype=bool), info)
 
     def legal_ids_padded(self):
         """The agent's legal action ids as they come off the device: ``(ids uint16 [num_envs, width], counts int32
@@ -217,6 +326,11 @@ class BlokusVectorEnv:
 
     def close(self):
         self.states = None
+
+
+def _cudart():
+    from .backend import _cudart as find
+    return find()
 
 
 class _Bufs:

@@ -68,26 +68,52 @@ def test_colosseum_shim_surface_on_gpu(engine20, oracle20):
         shim.set_backend(None)
 
 
-def test_vector_env_on_gpu_matches_cpu_stand_in():
+@pytest.mark.parametrize("N,P,agent,narrow", [(7, 2, 0, False), (7, 4, 2, False), (7, 2, 0, True), (20, 4, 0, True)])
+def test_vector_env_on_gpu_matches_cpu_stand_in(N, P, agent, narrow):
+    """`step` on the CUDA engine (direct C-ABI launches, host-side episode statistics) against the same class over the CPU
+    stand-in engine (generic path): observations, rewards, done flags, legal ids, episode statistics and final observations,
+    step by step; `narrow` starts with id rows that are too short, so the staging buffers are replaced mid-step."""
     from blokus_rl_b200 import BlokusEngine
     from blokus_rl_b200.vector_env import BlokusVectorEnv
-    envs = [BlokusVectorEnv(16, engine=BlokusEngine(7, 2), seed=11), BlokusVectorEnv(16, engine=OracleEngine(7, 2), seed=11)]
+    E = 16 if N == 7 else 6
+    envs = [BlokusVectorEnv(E, engine=BlokusEngine(N, P), seed=11, agent_player=agent),
+            BlokusVectorEnv(E, engine=OracleEngine(N, P), seed=11, agent_player=agent)]
+    assert envs[0]._direct and not envs[1]._direct
+    if narrow:
+        envs[0]._idx_stride = 8
+        envs[0]._alloc_idx()
     obs = [e.reset()[0] for e in envs]
     assert (obs[0] == obs[1]).all()
     rng = np.random.default_rng(1)
     episodes = 0
-    for _ in range(30):
+    for _ in range(30 if N == 7 else 24):
         poss = [e.get_attr("ai_possible_indexes") for e in envs]
         assert poss[0] == poss[1]
         acts = np.array([rng.choice(p) for p in poss[0]])
         res = [e.step(acts) for e in envs]
         for k in range(4):
-            assert (res[0][k] == res[1][k]).all()
+            assert res[0][k].dtype == res[1][k].dtype and (res[0][k] == res[1][k]).all()
         episodes += int(res[0][2].sum())
-        if res[0][2].any():
-            for i in np.flatnonzero(res[0][2]):
-                assert res[0][4]["final_info"][i] == res[1][4]["final_info"][i]
-    assert episodes > 16
+        assert ("final_info" in res[0][4]) == bool(res[0][2].any()) == ("final_info" in res[1][4])
+        for i in np.flatnonzero(res[0][2]):
+            assert res[0][4]["final_info"][i] == res[1][4]["final_info"][i]
+            assert (res[0][4]["final_observation"][i] == res[1][4]["final_observation"][i]).all()
+    assert episodes > (16 if N == 7 else 0)
+    assert (envs[0].states.cpu() == envs[1].states.cpu()).all()
+    if narrow:
+        assert envs[0]._idx_stride > 8
+    # an illegal action for ONE env raises and leaves every env where it was
+    poss = envs[0].get_attr("ai_possible_indexes")
+    acts = np.array([p[0] for p in poss])
+    acts[3] = next(a for a in range(envs[0].A) if a not in set(poss[3]))
+    before = envs[0].states.clone()
+    with pytest.raises(ValueError):
+        envs[0].step(acts)
+    assert (envs[0].states == before).all() and envs[0].get_attr("ai_possible_indexes") == poss
+    acts[3] = poss[3][-1]
+    res = [e.step(acts) for e in envs]
+    for k in range(4):
+        assert (res[0][k] == res[1][k]).all()
 
 
 def test_random_play_shards_match_cpu_stand_in_and_are_partition_invariant(engine7):
