@@ -957,8 +957,10 @@ __device__ __forceinline__ int playout_game(EnvRegs &e, const SmemTables &tb, co
     cand = cand == 0 ? P - 1 : cand - 1;
     int tries = 1;
     uint32_t stuck = 0u;
+    // (a game has at most 21 placements per player: the bound only matters if the state handed in was not a reachable one,
+    // and then it keeps the kernel from spinning)
 #pragma unroll 1
-    while (!over) {
+    while (!over && nply <= 21 * P) {
         cand = (cand + 1 == P) ? 0 : cand + 1;
         bool has = false;
         int mine = 0, incl = 0;
@@ -1022,6 +1024,10 @@ __global__ void __launch_bounds__(kRollWarps * 32, BLK_ROLL_MIN_BLOCKS) rollout_
     const int P = g.P;
     const int sw = P * g.N + P + 4;
     const int64_t total = a.n_roots * a.per_root;
+    // the chunked readers of the staged fields (count_field_chunk at N = 14) read the padding behind the last field: it
+    // must hold zeros, whatever the previous kernel left in this shared memory
+    for (int i = geo_nf<kN>(gg) + lane; i < geo_fld_words<kN>(gg); i += 32) fld[i] = 0u;
+    __syncwarp();
 
     for (int64_t gid = next_ticket(rp.queue, lane); gid < total; gid = next_ticket(rp.queue, lane)) {
         const int64_t root = gid / a.per_root;

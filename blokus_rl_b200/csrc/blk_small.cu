@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kRT, 2) small_rollout_kernel(const SmallRollPa
         cand = cand == 0 ? P - 1 : cand - 1;          // the root's mover is evaluated first
         int tries = 1;
         uint32_t stuck = 0u;
-        while (!over) {
+        while (!over && nply <= 21 * P) {          // (bounded: an unreachable input state cannot spin the kernel)
             cand = (cand + 1 == P) ? 0 : cand + 1;
             int cnt = 0;
             if (!((stuck >> cand) & 1u)) {

@@ -228,6 +228,39 @@ def test_unaligned_and_contiguous_bool_mask(engine20, oracle20, engine7):
                 assert (raw[base_off: base_off + n * stride].view(n, stride)[:, A:] == 7).all()   # nor between them
 
 
+@pytest.mark.parametrize("N,P", [(14, 2), (14, 4), (12, 2), (20, 4)])
+def test_playouts_do_not_depend_on_what_shared_memory_held(N, P, engine20):
+    """Playouts on every SM right after kernels with another shared-memory layout ran there (the chunked field readers of the
+    14x14 kernel read the padding behind the last field: it must be zeroed by the kernel itself, not by luck).  Enough
+    playouts to occupy the whole GPU; a strided sample is replayed by the oracle, all of them must be complete games."""
+    from blokus_rl_b200 import BlokusEngine
+    from oracle.oracle import Oracle
+    import ctypes as C
+    import torch
+    # dirty the shared memory of every SM: 20x20 byte-mask steps (fields + tables + LUT at other offsets)
+    s20 = engine20.new_states(16384)
+    o = engine20.step(s20, None, mask="bytes", sample=True, seed=1)
+    for _ in range(6):
+        o = engine20.step(s20, o.next_action, mask="bytes", sample=True, seed=1)
+    eng, orc = BlokusEngine(N, P), Oracle(N, P)
+    roots = eng.new_states(64)
+    o = eng.step(roots, None, mask=None, sample=True, seed=3)
+    for _ in range(6):
+        o = eng.step(roots, o.next_action, mask=None, sample=True, seed=3)
+    per_root, seed = 128, 99
+    out = eng.rollout(roots, per_root, seed=seed)
+    torch.cuda.synchronize()
+    fs, pl, win = out.final_scores.cpu().numpy(), out.plies.cpu().numpy(), out.winners.cpu().numpy()
+    assert (win != 0).all() and (pl > 0).all() and (pl <= 21 * P).all()
+    host = orc.unpack_many(roots.cpu().numpy())
+    for r in range(0, 64, 4):
+        root = C.create_string_buffer(host[r].tobytes(), orc.state_size)
+        for j in range(0, per_root, 16):
+            n, scores, _, _, _ = orc.playout(root, seed, r * per_root + j)
+            assert n == pl[r, j] and (scores == fs[r, j]).all()
+    eng.close()
+
+
 def test_rollouts_replay_through_oracle(engine20, oracle20):
     import torch
     orc = oracle20

@@ -15,7 +15,8 @@ total_steps = total_games = 0
 t0 = time.time()
 for (N, P, rule, n, plies, seed) in ((7, 2, 1, 800, 100, 21), (6, 4, 0, 400, 80, 22), (5, 4, 1, 400, 60, 23), (6, 2, 1, 400, 80, 24), (20, 4, 0, 1500, 200, 11), (20, 4, 1, 600, 150, 12), (20, 2, 0, 400, 120, 13),
                                      (14, 2, 1, 800, 150, 14), (14, 4, 0, 500, 150, 15), (7, 2, 0, 1500, 120, 16),
-                                     (7, 4, 0, 400, 100, 17), (10, 2, 1, 400, 120, 18), (5, 2, 0, 400, 60, 19)):
+                                     (7, 4, 0, 400, 100, 17), (10, 2, 1, 400, 120, 18), (5, 2, 0, 400, 60, 19),
+                                     (12, 4, 0, 300, 120, 25), (13, 2, 1, 300, 120, 26), (15, 4, 0, 300, 140, 27), (16, 2, 0, 300, 140, 28)):
     eng, orc = BlokusEngine(N, P, score_rule=rule), Oracle(N, P, rule)
     steps, games = lockstep(eng, orc, n=int(n * scale), plies=plies, seed=seed, env_id_base=seed * 100000, check_naive_every=1009)
     print(f"{N}x{N} {P}p rule {rule}: {steps} steps, {games} games finished -- bit-exact (states, masks bytes+bits, counts, flags, "
