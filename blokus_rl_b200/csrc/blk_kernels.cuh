@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                          : kN == 14 ? (13729 + BLK_ROW_ALIGN - 1) / BLK_ROW_ALIGN * BLK_ROW_ALIGN : gg.mask_bytes;
     const int gather = geo_gather<kN>(gg);
     uint32_t *fld = reinterpret_cast<uint32_t *>(scratch + static_cast<size_t>(warp) * gg.warp_smem);
-    uint32_t *tots = fld + fld_words;                                  // 32 per-pass popcount totals (sampler)
+    // (the 32 words behind the fields are scratch: lanes >= N of the unconditional field stores land there)
     const int64_t n = a.n;
     const int64_t mstride = a.mask_stride;
     const bool want_count = a.legal_count != nullptr;
@@ -765,6 +765,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
         // ---- gather the action-id-ordered mask from the staged fields and stream it out ----
         int cnt = 0;
         int idx_pick = -1;
+        int fmine = 0, fincl = 0;                      // this lane's legal count over its chunk of fields, and the warp scan of it
         if (kFmt == 4) {
             // Index list: the ids come straight out of the fields (field order is id order), no mask words are built.
             // Every lane counts its contiguous chunk of fields, a scan gives it its first slot, and it writes its ids there.
@@ -816,25 +817,29 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                 idx_pick = static_cast<int>(tb.foff[fsel]) + bit;
             }
         } else if (kFmt != 0 || kSample || want_count) {
+            // The sampler (and a count without a mask) reads the legal set straight from the fields, like the index-list format:
+            // one counting pass + one warp scan instead of POPC + REDUX + STS in every emit pass, and the emit loop below is left
+            // without a cross-lane operation (the REDUX latency sat on its critical path).
+            constexpr bool kFromFields = kSample || kFmt == 0;
+            if (kFromFields) {
+                const int nf_ = geo_nf<kN>(gg);
+                const int per = fields_per_lane<kN>(nf_);
+                fmine = count_field_chunk<kN>(fld, nf_, per, lane);
+                fincl = warp_incl_scan(fmine, lane);
+                cnt = __shfl_sync(kAllLanes, fincl, 31);
+            }
             unsigned char *row = reinterpret_cast<unsigned char *>(a.mask) + env * mstride + 16 * lane;
             uint32_t *wrow = reinterpret_cast<uint32_t *>(a.mask) + env * mstride + lane;
             unsigned char *urow = reinterpret_cast<unsigned char *>(a.mask) + env * mstride;     // kFmt == 3 only
             const int ush = static_cast<int>(reinterpret_cast<uintptr_t>(urow) & 15);
             uint32_t uprev = 0u;
 #pragma unroll(kEmitUnroll)
-            for (int r = 0; r < rounds; ++r) {
+            for (int r = 0; r < (kFmt == 0 && kFromFields ? 0 : rounds); ++r) {
                 uint32_t word;
                 if (gather == 3) word = assemble_word3(r << 5, fld, wdl);
                 else if (gather == 5) word = assemble_word5(r << 5, fld, wdl);
                 else word = ((r << 5) + lane) < mw ? assemble_word((r << 5) + lane, fld, tb.foff, tb.wsrc) : 0u;
-                const int pc = __popc(word);
-                if (kSample) {
-                    const int tot = __reduce_add_sync(kAllLanes, pc);
-                    if (lane == 0) tots[r] = tot;
-                    cnt += tot;
-                } else {
-                    cnt += pc;
-                }
+                if (!kFromFields) cnt += __popc(word);
                 if (kFmt == 4) {
                     // (handled above, straight from the fields)
                 } else if (kFmt == 1) {
@@ -880,7 +885,7 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
                     uprev = __shfl_sync(kAllLanes, word, 31);
                 }
             }
-            if (!kSample) cnt = warp_sum(cnt);
+            if (!kFromFields) cnt = warp_sum(cnt);
         }
         if (want_count && lane == 0) a.legal_count[env] = cnt;
 
@@ -888,28 +893,14 @@ __global__ void __launch_bounds__(kWarps * 32, BLK_MIN_BLOCKS) step_kernel(const
         if (kSample) {
             int pick = idx_pick;
             if (kFmt != 4 && cnt > 0) {
-                __syncwarp();
                 const uint32_t ply = e.meta >> 16;
                 const uint32_t u = philox_word(philox4(ply >> 2, e.game, 0u, 0u, static_cast<uint32_t>(a.seed),
                                                        static_cast<uint32_t>(a.seed >> 32) ^ (a.env_id_base + static_cast<uint32_t>(env))), ply);
-                int k = static_cast<int>(__umulhi(u, static_cast<uint32_t>(cnt)));
-                // level 1: which pass of 32 words
-                const int tot = lane < rounds ? static_cast<int>(tots[lane]) : 0;
-                const int incl = warp_incl_scan(tot, lane);
-                const int R = __ffs(__ballot_sync(kAllLanes, k < incl)) - 1;
-                k -= __shfl_sync(kAllLanes, incl - tot, R);
-                // level 2: which word of that pass (re-gathered: cheaper than keeping 952 popcounts around)
-                const int gi = (R << 5) + lane;
-                uint32_t word;
-                if (gather == 3) word = assemble_word3(gi, fld, tb.wdesc);
-                else if (gather == 5) word = assemble_word5(gi, fld, tb.wdesc);
-                else word = gi < mw ? assemble_word(gi, fld, tb.foff, tb.wsrc) : 0u;
-                const int c2 = __popc(word);
-                const int incl2 = warp_incl_scan(c2, lane);
-                const int J = __ffs(__ballot_sync(kAllLanes, k < incl2)) - 1;
-                k -= __shfl_sync(kAllLanes, incl2 - c2, J);
-                const uint32_t wsel = __shfl_sync(kAllLanes, word, J);
-                pick = (((R << 5) + J) << 5) + kth_set_bit_warp(wsel, k, lane);
+                const int nf_ = geo_nf<kN>(gg);
+                int bit;
+                const int fsel = kth_legal_field<kN>(fld, static_cast<int>(__umulhi(u, static_cast<uint32_t>(cnt))), fmine, fincl, nf_,
+                                                     fields_per_lane<kN>(nf_), lane, bit);
+                pick = static_cast<int>(tb.foff[fsel]) + bit;
             }
             if (lane == 0) a.next_action[env] = pick;
         }
