@@ -64,3 +64,13 @@ def test_gpu_arm_search_workload_lines():
     assert p["unit"] == "simulations/s" and p["value"] > 1e4 and p["counters"]["overflow"] == 0 and p["e2e"]["d2h_bytes_per_step"] == 4 * 64
     q = _run("--workload", "puct", "--steps", "2", "--roots", "1", "--sims", "50", "--warps-per-tree", "8")
     assert q["value"] > 1e4 and "8 warp(s) per tree" in q["config"]["workload"]
+
+
+def test_committed_ncu_traffic_is_that_of_the_current_kernel_sources():
+    """`roofline.traffic` comes from profiles/traffic.json, which `tools/profile_all.py --summarise` stamps with the hash of the
+    kernel sources it captured; bench.py nulls an entry with another stamp.  The committed record must be the current one:
+    after an edit under csrc/ (or of the header), re-capture (tools/gpu/README.md) before committing."""
+    from blokus_rl_b200.build import kernel_source_hash
+    rec = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+    assert rec["source_hash"] == kernel_source_hash(), "profiles/traffic.json was captured from other kernel sources"
+    assert {"step_kernel_20_4_bytes_65536", "step_kernel_20_4_bits_65536", "rollout_kernel_20_4", "step_kernel_7_2_bytes_1048576"} <= set(rec["kernels"])
